@@ -1,0 +1,216 @@
+/*
+ * vcg.h -- C ABI of libvcg_b200.so: the sm_100a kernels behind the VAE-CycleGAN training step.
+ *
+ * The reference (Baverne/VAE-CYCLEGAN-Implementation) is pure Python/PyTorch and has no FFI of
+ * its own; every entry point below replaces an ATen call that the reference issues implicitly
+ * from Networks.py / Losses.py / torch.optim.Adam.  The reference call site each one stands
+ * in for is cited (file:line relative to the reference checkout; "torch/" = site-packages/torch).
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, <0 (VCG_E_*) on failure, never
+ *     throws/aborts; the message is available through vcg_last_error() (thread local).
+ *   - the caller owns every buffer (device pointers from tensor.data_ptr()); the library never
+ *     allocates, frees or retains device memory.
+ *   - all work is enqueued on the cudaStream_t passed as `void* stream`; no hidden sync, no
+ *     default-stream use; every call is CUDA-graph capturable.
+ *   - unsupported shape / dtype => VCG_E_UNSUPPORTED.  There is no CPU fallback.
+ *
+ * Activation layout in HBM: NHWC, element type VCG_F32 (parity mode) or VCG_BF16 (tensor-core
+ * mode).  A convolution reads a *materialised* halo: its input buffer is [N, Hp, Wp, C] with the
+ * reflect (forward) or zero (data-gradient) border already written by vcg_xform_fwd / bwd, so
+ * every convolution is a "valid" stride-1 correlation (stride-2 4x4 convolutions are expressed
+ * as 2x2 stride-1 ones over a space-to-depth input; PixelUnshuffle/PixelShuffle are folded into
+ * the addressing of vcg_xform_*).
+ */
+#ifndef VCG_H_
+#define VCG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VCG_ABI_VERSION 1
+#define VCG_API __attribute__((visibility("default")))
+
+enum { VCG_OK = 0, VCG_E_INVALID = -1, VCG_E_UNSUPPORTED = -2, VCG_E_CUDA = -3, VCG_E_DRIVER = -4 };
+enum { VCG_F32 = 0, VCG_BF16 = 1 };
+enum { VCG_ACT_NONE = 0, VCG_ACT_RELU = 1, VCG_ACT_LEAKY = 2 };          /* LeakyReLU slope 0.2 */
+/* vcg_xform_* addressing modes (destination domain of the forward transform) */
+enum { VCG_MODE_PLAIN = 0,      /* dst[h,w,c]            = src[h,w,c]                              */
+       VCG_MODE_SHUFFLE = 1,    /* dst[2h+i,2w+j,c]      = src[h,w,c*4+i*2+j]   (nn.PixelShuffle)   */
+       VCG_MODE_UNSHUFFLE = 2,  /* dst[h,w,(i*2+j)*C+c]  = src[2h+i,2w+j,c]     (nn.PixelUnshuffle) */
+       VCG_MODE_PAD_S2D = 3 };  /* reflect-pad first, then space-to-depth (stride-2 conv input)    */
+/* weight (un)packing channel maps */
+enum { VCG_WMAP_PLAIN = 0, VCG_WMAP_UNSHUFFLE = 1, VCG_WMAP_S2D = 2 };
+
+VCG_API int vcg_version(void);
+VCG_API const char* vcg_last_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
+VCG_API long long vcg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Convolution as implicit GEMM.  Replaces F.pad(reflect)+F.conv2d issued by every
+ * nn.Conv2d(padding_mode='reflect') (Networks.py:60,87,101,104,122,136,145;
+ * torch/nn/modules/conv.py:534-550) and the autograd convolution_backward behind it.        */
+typedef struct vcg_conv_desc {
+  int32_t dtype;      /* VCG_F32: SIMT FFMA kernels; VCG_BF16: tcgen05/TMEM kernels, fp32 accumulate */
+  int32_t n;          /* images */
+  int32_t hp, wp;     /* input buffer spatial dims (halo included) */
+  int32_t c;          /* physical channels per input pixel (multiple of 8) */
+  int32_t kh, kw;     /* filter taps (stride 1) */
+  int32_t kwc_pad;    /* packed filter row length per kh: roundup(kw*c, 64) */
+  int32_t cout;       /* logical output channels (bias/activation/stats bound); stores are rounded up to 8 */
+  int32_t cout_pad;   /* packed filter rows (multiple of 16, >= cout) */
+  int32_t out_c;      /* physical channels per output pixel */
+  int32_t act;        /* VCG_ACT_* applied after bias, before stats */
+  int32_t stats;      /* !=0: accumulate per-(n,cout) sum / sum-of-squares of the stored values */
+  int32_t flat;       /* !=0: tile the output in flattened input-pitch order (data-gradient) */
+  int32_t out_f32;    /* !=0: store y as fp32 even when dtype is VCG_BF16 (final image layer) */
+} vcg_conv_desc;
+
+/* y[n,h,w,co] = act(bias[co] + sum_{kh,j} x[n,h+kh,w*c + j] * w[co,kh,j]),  h<hp-kh+1, w<wp-kw+1.
+ * x: [n,hp,wp,c]; w: [cout_pad,kh,kwc_pad] (dtype); bias: fp32[cout] or NULL; y: [n,ho,wo,out_c];
+ * stats: fp32 [n,cout,2] accumulators (+=) or NULL.  The data-gradient pass is the same call
+ * with the flipped/transposed packed filter and a zero-haloed dy as x.                       */
+VCG_API int vcg_conv_fwd(const vcg_conv_desc* d, const void* x, const void* w, const float* bias,
+                 void* y, float* stats, void* stream);
+
+/* dw[co,kh,j] += sum_{n,h,w} dy[n,h+kh-1.., ...] ...: weight gradient, fp32 packed layout
+ * [cout_pad,kh,kwc_pad], ACCUMULATED (split-K reductions use red.global.add).
+ * x: the forward input [n,hp,wp,c]; dy: [n, ho+2*dy_halo, wo+2*dy_halo, dy_c] zero-haloed.      */
+VCG_API int vcg_conv_wgrad(const vcg_conv_desc* d, const void* x, const void* dy, int32_t dy_halo,
+                   int32_t dy_c, float* dw, void* stream);
+
+/* Filter packing: reference OIHW fp32 master weight -> packed kernel layout, and back for grads.
+ * transpose_flip=0: rows=co, K=(kh,kw,phys cin) (forward); 1: rows=phys cin, K=(flipped kh,kw,co)
+ * (data-gradient).  wmap says how physical input channels map to (ci, sub-tap).              */
+typedef struct vcg_wpack_desc {
+  int32_t dtype;            /* element type of the packed filter */
+  int32_t co, ci, kh, kw;   /* reference OIHW dims */
+  int32_t wmap;             /* VCG_WMAP_* */
+  int32_t c_phys;           /* physical input channels of the conv as executed (>= mapped channels) */
+  int32_t co_phys;          /* physical output channels (data-gradient K extent) */
+  int32_t rows_pad;         /* packed rows */
+  int32_t pkh, pkw;         /* taps as executed (kh/2, kw/2 for S2D) */
+  int32_t kwc_pad;          /* packed row length per tap row */
+  int32_t transpose_flip;
+} vcg_wpack_desc;
+VCG_API int vcg_wpack(const vcg_wpack_desc* d, const float* w_oihw, void* packed, void* stream);
+/* grad_oihw (=|+=) unpack(dw_packed fp32 forward layout) */
+VCG_API int vcg_wunpack_grad(const vcg_wpack_desc* d, const float* dw_packed, float* grad_oihw,
+                     int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* InstanceNorm statistics (nn.InstanceNorm2d, Networks.py:61,88,102,105,123 -> native_batch_norm) */
+/* mean/rstd[n,c] from a dense NHWC tensor (fp64 accumulation; parity mode and tests).
+ * mean_rstd must have room for n*c*2 floats FOLLOWED BY n*c*2 doubles of scratch (3x the floats). */
+VCG_API int vcg_in_stats(int32_t dtype, const void* y, int32_t n, int32_t hw, int32_t c, int32_t c_pitch,
+                 float* mean_rstd, void* stream);
+/* mean/rstd[n,c] from the (sum,sumsq) accumulators a conv epilogue produced; eps=1e-5, biased var */
+VCG_API int vcg_in_finalize(const float* sums, int32_t nc, int32_t hw, float* mean_rstd, void* stream);
+
+/* The memory-bound pass between two convolutions: normalise -> activation -> (+residual) ->
+ * pixel (un)shuffle / space-to-depth addressing -> reflect halo -> cast.  Replaces
+ * instance_norm, ReLU/LeakyReLU, pixel_(un)shuffle, reflection_pad2d and the residual add
+ * (Networks.py:76-81, 91-96, 108-116, 126-131).                                               */
+typedef struct vcg_xform_desc {
+  int32_t dtype;
+  int32_t n, h, w, c;        /* source logical dims */
+  int32_t src_c;             /* source physical channel pitch */
+  int32_t norm;              /* use mean_rstd[n,c] */
+  int32_t act;               /* VCG_ACT_* after the norm */
+  int32_t mode;              /* VCG_MODE_* */
+  int32_t pad;               /* reflect halo width (destination domain; PAD_S2D: source domain) */
+  int32_t dst_c;             /* destination physical channel pitch (extra channels zero-filled) */
+  int32_t res_hp, res_wp, res_c, res_off;  /* residual: [n,res_hp,res_wp,res_c] read at (+off,+off) */
+} vcg_xform_desc;
+VCG_API int vcg_xform_fwd(const vcg_xform_desc* d, const void* src, const float* mean_rstd,
+                  const void* residual, void* dst, void* stream);
+
+/* Backward of the same pass, phase 1: g = sum_k gather(dxp_k) (halo folded, shuffle inverted),
+ * then the activation derivative; writes g into the interior of the zero-haloed dy buffer
+ * [n,h+2*dy_halo,w+2*dy_halo,dy_c] and accumulates sum(g), sum(g*zhat) per (n,c) for phase 2.
+ * Without norm it also applies the pre-norm activation mask (y>0) and accumulates dbias.       */
+typedef struct vcg_gsrc {      /* one gradient source = padded-input gradient of a consumer conv */
+  const void* dxp;             /* [n, *, *, c_pitch] in the consumer's destination domain */
+  int32_t mode, pad, c_pitch;
+} vcg_gsrc;
+typedef struct vcg_xbwd_desc {
+  int32_t dtype;
+  int32_t n, h, w, c;
+  int32_t y_c;               /* physical pitch of the saved conv output y */
+  int32_t norm, act;         /* as in the forward desc (act = post-norm activation) */
+  int32_t pre_act;           /* activation fused in the conv epilogue (before the norm) */
+  int32_t dy_halo, dy_c;     /* destination geometry */
+  int32_t nsrc;              /* 1..3 */
+} vcg_xbwd_desc;
+VCG_API int vcg_xform_bwd_gather(const vcg_xbwd_desc* d, const vcg_gsrc* srcs, const void* y,
+                         const float* mean_rstd, void* dy, float* gsums /*[n,c,2]*/,
+                         float* dbias /*[c] or NULL*/, void* stream);
+/* phase 2 (norm only), in place on dy: v = rstd*(g - mean(g) - zhat*mean(g*zhat)) * pre_act'(y) */
+VCG_API int vcg_xform_bwd_norm(const vcg_xbwd_desc* d, const void* y, const float* mean_rstd,
+                       const float* gsums, void* dy, float* dbias, void* stream);
+
+/* NCHW fp32 <-> NHWC(dtype) with channel pitch/offset: the API boundary of a network */
+VCG_API int vcg_pack_nchw(int32_t dtype, const float* src, int32_t n, int32_t c, int32_t h, int32_t w,
+                  void* dst, int32_t dst_c, int32_t dst_halo, void* stream);  /* zero halo + pad channels */
+VCG_API int vcg_unpack_nchw(int32_t dtype, const void* src, int32_t src_c, int32_t n, int32_t c,
+                    int32_t h, int32_t w, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* VAE reparameterisation + KL (Networks.py:219-227, Losses.py:115-121).                       */
+/* z = mu + eps*exp(0.5*clamp(lv,-10,10)); logvar_out = clamp(lv); kl_sum += sum(1+lv-mu^2-e^lv) */
+VCG_API int vcg_reparam_fwd(int32_t dtype, const void* mu, int32_t mu_pitch, const void* lv, int32_t lv_pitch,
+                    const float* eps /*NCHW fp32*/, int32_t n, int32_t hw, int32_t c,
+                    void* z /*dense NHWC c*/, float* mu_out /*NCHW*/, float* lv_out /*NCHW*/,
+                    float* kl_sum, void* stream);
+/* dmu = dz + gmu_ext + kl_scale*mu ; dlv = mask*(dz*eps*0.5*std + glv_ext - 0.5*kl_scale*(1-e^lv)) */
+VCG_API int vcg_reparam_bwd(int32_t dtype, const void* mu, int32_t mu_pitch, const void* lv, int32_t lv_pitch,
+                    const float* eps, const void* dz, int32_t dz_pitch,
+                    const float* gmu_ext /*NCHW or NULL*/, const float* glv_ext /*NCHW or NULL*/,
+                    float kl_scale, int32_t n, int32_t hw, int32_t c,
+                    void* dmu, int32_t dmu_pitch, void* dlv, int32_t dlv_pitch, void* stream);
+
+/* Fused losses on fp32 tensors (Losses.py:14-121).  Each writes the *sum* into out[0] (+=) and,
+ * when grad != NULL, grad = scale * d(sum)/d(a).                                              */
+VCG_API int vcg_l1_fwd_bwd(const float* a, const float* b, int64_t numel, float scale, float* out_sum,
+                   float* grad_a, void* stream);                      /* sum |a-b|, scale*sign(a-b) */
+VCG_API int vcg_mse_const_fwd_bwd(const float* d, int64_t numel, float target, float scale,
+                          float* out_sum, float* grad_d, void* stream); /* sum (d-t)^2, scale*2(d-t) */
+VCG_API int vcg_kl_fwd_bwd(const float* mu, const float* lv, int64_t numel, float scale, float* out_sum,
+                   float* gmu, float* glv, void* stream);
+
+/* Spectral-normalised 512->1 16x16 head (Networks.py:248,267-269;
+ * torch/nn/utils/spectral_norm.py:92-114): score[n] = bias + <x[n], w>/||w||.                   */
+VCG_API int vcg_dhead_fwd(int32_t dtype, const void* x /*[n,k] NHWC-flattened*/, const float* w_khwc,
+                  const float* bias, int32_t n, int32_t k, float* score, float* wnorm2 /*[1]*/,
+                  void* stream);
+/* dx[n,:] = gs[n]*w/||w||; dw += (G - (G.w_hat) w_hat)/||w|| with G = sum_n gs[n] x[n]; dbias += sum gs */
+VCG_API int vcg_dhead_bwd(int32_t dtype, const void* x, const float* w_khwc, const float* wnorm2,
+                  const float* gscore, int32_t n, int32_t k, void* dx, float* dw, float* dbias,
+                  float* scratch /*[k+1]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Multi-tensor Adam (torch/optim/adam.py:457-547 as called from Networks.py:312,894,1032-1033,
+ * 1669-1676,1928-1935): one launch over a table of tensors.                                    */
+typedef struct vcg_adam_chunk {  /* one <=65536-element slice of one tensor */
+  float* p; const float* g; float* m; float* v; int32_t numel;
+} vcg_adam_chunk;
+VCG_API int vcg_adam_multi(const vcg_adam_chunk* chunks_dev, int32_t nchunks, float lr, float beta1,
+                   float beta2, float eps, float bias_corr1, float bias_corr2_sqrt,
+                   float grad_scale, void* stream);
+
+/* test hook: encode a bf16 SWIZZLE_128B tiled TMA descriptor only (no launch) */
+VCG_API int vcg_probe_tmap(const void* base, int32_t rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box);
+
+/* utility: fill fp32 zeros (graph-capturable memset wrapper) */
+VCG_API int vcg_zero(void* p, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCG_H_ */

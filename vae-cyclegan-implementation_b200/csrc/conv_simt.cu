@@ -1,0 +1,204 @@
+// conv_simt.cu -- fp32 "parity mode" convolution kernels (FFMA, fp32 accumulate), sm_100a.
+//
+// north_star asks for 1e-5 parity in fp32 mode; tcgen05 offers only tf32 (~5e-4 per op) for fp32
+// data, so the fp32 mode runs these shared-memory tiled SIMT implicit GEMMs over exactly the same
+// buffer layouts as the tensor-core kernels (NHWC with materialised halo, packed filters).  They
+// are also instantiated for bf16 storage for the few degenerate layers the tensor-core kernels do
+// not take (e.g. the weight gradient of the 64->3 7x7 output convolution, M = 3).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+struct SimtArgs {
+  int n, hp, wp, c, kh, kw, kwc_pad, ho, wo, cout, out_c, act, out_f32;
+  long long npix;
+};
+
+// y[pix, co] = act(bias + sum_{kh} sum_{j<kw*c} x[(n,h+kh,w), j] * w[co][kh][j])
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_fwd_simt_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                     void* __restrict__ y, SimtArgs p) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const long long m0 = static_cast<long long>(blockIdx.x) * TM;
+  const int n0 = blockIdx.y * TN;
+  const int tx = tid & 15, ty = tid >> 4;   // 16 x 16 threads, 4x4 outputs each
+  float acc[4][4] = {};
+  const int kwc = p.kw * p.c;
+  // loader mapping: 256 threads load 64 rows x 16 k -> 4 elements each (row = tid/4, k = (tid%4)*4..)
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+  const long long pixA = m0 + lrow;
+  long long abase = -1;
+  if (pixA < p.npix) {
+    const int wq = static_cast<int>(pixA % p.wo);
+    const long long t = pixA / p.wo;
+    const int hq = static_cast<int>(t % p.ho);
+    const int nq = static_cast<int>(t / p.ho);
+    abase = ((static_cast<long long>(nq) * p.hp + hq) * p.wp + wq) * p.c;
+  }
+  const int coB = n0 + lrow;
+  for (int khi = 0; khi < p.kh; ++khi) {
+    const long long arow = abase + static_cast<long long>(khi) * p.wp * p.c;
+    const long long brow = (static_cast<long long>(coB) * p.kh + khi) * p.kwc_pad;
+    for (int j0 = 0; j0 < kwc; j0 += TK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = j0 + lk + i;
+        float av = 0.f, bv = 0.f;
+        if (j < kwc) {
+          if (abase >= 0) av = Elem<T>::ld(x + arow + j);
+          if (coB < p.cout) bv = Elem<T>::ld(w + brow + j);
+        }
+        As[lk + i][lrow] = av;
+        Bs[lk + i][lrow] = bv;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < TK; ++k) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long pix = m0 + ty * 4 + i;
+    if (pix >= p.npix) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + tx * 4 + j;
+      if (co >= p.cout) continue;
+      float v = acc[i][j] + (bias ? bias[co] : 0.f);
+      v = act_apply(v, p.act);
+      if (p.out_f32) reinterpret_cast<float*>(y)[pix * p.out_c + co] = v;
+      else Elem<T>::st(reinterpret_cast<T*>(y) + pix * p.out_c + co, v);
+    }
+  }
+}
+
+struct SimtWgradArgs {
+  int n, hp, wp, c, kh, kw, kwc_pad, ho, wo, cout, dy_halo, dy_c, pix_per_split;
+  long long npix;
+};
+
+// dw[co][kh][j] += sum_pix dy[pix, co] * x[(pix + kh rows), j];  grid = (j tiles, co tiles, kh*splits)
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, SimtWgradArgs p) {
+  __shared__ float As[TK][TM + 4];   // dy: [pixel k][co]
+  __shared__ float Bs[TK][TN + 4];   // x : [pixel k][j]
+  const int tid = threadIdx.x;
+  const int j0 = blockIdx.x * TN, co0 = blockIdx.y * TM;
+  const int khi = blockIdx.z % p.kh, split = blockIdx.z / p.kh;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4] = {};
+  const int kwc = p.kw * p.c;
+  const long long pbeg = static_cast<long long>(split) * p.pix_per_split;
+  long long pend = pbeg + p.pix_per_split;
+  if (pend > p.npix) pend = p.npix;
+  const int lk = tid >> 4, lcol = (tid & 15) * 4;   // 16 pixel rows x 64 columns, 4 each
+  const int wpd = p.wo + 2 * p.dy_halo, hpd = p.ho + 2 * p.dy_halo;
+  for (long long pk = pbeg; pk < pend; pk += TK) {
+    const long long pix = pk + lk;
+    long long xoff = -1, dyoff = -1;
+    if (pix < pend) {
+      const int wq = static_cast<int>(pix % p.wo);
+      const long long t = pix / p.wo;
+      const int hq = static_cast<int>(t % p.ho);
+      const int nq = static_cast<int>(t / p.ho);
+      xoff = ((static_cast<long long>(nq) * p.hp + hq + khi) * p.wp + wq) * p.c;
+      dyoff = ((static_cast<long long>(nq) * hpd + hq + p.dy_halo) * wpd + wq + p.dy_halo) * p.dy_c;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int co = co0 + lcol + i, j = j0 + lcol + i;
+      As[lk][lcol + i] = (dyoff >= 0 && co < p.cout) ? Elem<T>::ld(dy + dyoff + co) : 0.f;
+      Bs[lk][lcol + i] = (xoff >= 0 && j < kwc) ? Elem<T>::ld(x + xoff + j) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= p.cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int jj = j0 + tx * 4 + j;
+      if (jj >= kwc) continue;
+      atomicAdd(dw + (static_cast<long long>(co) * p.kh + khi) * p.kwc_pad + jj, acc[i][j]);
+    }
+  }
+}
+
+}  // namespace
+
+template <typename T>
+static int launch_fwd(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+                      int out_f32, cudaStream_t stream) {
+  SimtArgs a{};
+  a.n = d->n; a.hp = d->hp; a.wp = d->wp; a.c = d->c; a.kh = d->kh; a.kw = d->kw; a.kwc_pad = d->kwc_pad;
+  a.ho = d->hp - d->kh + 1; a.wo = d->wp - d->kw + 1; a.cout = d->cout; a.out_c = d->out_c; a.act = d->act;
+  a.out_f32 = out_f32;
+  a.npix = static_cast<long long>(d->n) * a.ho * a.wo;
+  dim3 grid(static_cast<unsigned>((a.npix + TM - 1) / TM), (d->cout + TN - 1) / TN);
+  conv_fwd_simt_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), static_cast<const T*>(w), bias, y, a);
+  VCG_CHECK_LAUNCH("conv_fwd_simt_kernel");
+  return VCG_OK;
+}
+
+int vcg_conv_fwd_simt(const vcg_conv_desc* d, int elem_dtype, const void* x, const void* w, const float* bias,
+                      void* y, int out_f32, cudaStream_t stream) {
+  VCG_REQUIRE(d->hp >= d->kh && d->wp >= d->kw, VCG_E_INVALID, "conv_simt: empty output");
+  if (elem_dtype == VCG_F32) return launch_fwd<float>(d, x, w, bias, y, 1, stream);
+  return launch_fwd<__nv_bfloat16>(d, x, w, bias, y, out_f32, stream);
+}
+
+template <typename T>
+static int launch_wgrad(const vcg_conv_desc* d, const void* x, const void* dy, int dy_halo, int dy_c, float* dw,
+                        cudaStream_t stream) {
+  SimtWgradArgs a{};
+  a.n = d->n; a.hp = d->hp; a.wp = d->wp; a.c = d->c; a.kh = d->kh; a.kw = d->kw; a.kwc_pad = d->kwc_pad;
+  a.ho = d->hp - d->kh + 1; a.wo = d->wp - d->kw + 1; a.cout = d->cout; a.dy_halo = dy_halo; a.dy_c = dy_c;
+  a.npix = static_cast<long long>(d->n) * a.ho * a.wo;
+  const int kwc = d->kw * d->c;
+  const int tiles = ((kwc + TN - 1) / TN) * ((d->cout + TM - 1) / TM) * d->kh;
+  long long splits = (4LL * vcg_num_sms() + tiles - 1) / tiles;
+  const long long max_splits = (a.npix + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  long long pps = (a.npix + splits - 1) / splits;
+  pps = ((pps + TK - 1) / TK) * TK;
+  splits = (a.npix + pps - 1) / pps;
+  a.pix_per_split = static_cast<int>(pps);
+  dim3 grid((kwc + TN - 1) / TN, (d->cout + TM - 1) / TM, static_cast<unsigned>(d->kh * splits));
+  conv_wgrad_simt_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), static_cast<const T*>(dy), dw, a);
+  VCG_CHECK_LAUNCH("conv_wgrad_simt_kernel");
+  return VCG_OK;
+}
+
+int vcg_conv_wgrad_simt(const vcg_conv_desc* d, int elem_dtype, const void* x, const void* dy, int dy_halo,
+                        int dy_c, float* dw, cudaStream_t stream) {
+  if (elem_dtype == VCG_F32) return launch_wgrad<float>(d, x, dy, dy_halo, dy_c, dw, stream);
+  return launch_wgrad<__nv_bfloat16>(d, x, dy, dy_halo, dy_c, dw, stream);
+}

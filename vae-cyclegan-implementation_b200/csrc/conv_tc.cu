@@ -1,0 +1,329 @@
+// conv_tc.cu -- implicit-GEMM convolution on 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// One persistent, warp-specialised kernel serves the forward pass and the data-gradient pass of
+// every convolution of the reference (Networks.py:60,87,101,104,122,136,145 executed through
+// torch/nn/modules/conv.py:534-550 and autograd's convolution_backward):
+//
+//   D[pixel, cout] = sum_{kh} sum_{j < kw*c} X[n, h+kh, (w*c + j)] * W[cout, kh, j]
+//
+//   A operand  = X, NHWC bf16 with a materialised halo: a [tw x th] box of output pixels at tap
+//                (kh,kw) and channel chunk q is ONE 4-D TMA box load shifted by (kw,kh) -- 128 rows of
+//                64 bf16 land in shared memory in exactly the K-major SWIZZLE_128B UMMA layout.
+//                "window" maps (dim0 = kw*c with an overlapping pixel stride) serve thin inputs
+//                (c = 8/16/32); "flat" maps tile the output in input-pitch order (data gradient).
+//   B operand  = packed filter [cout_pad][kh][kwc_pad] bf16, 2-D TMA boxes of 64 x BN.
+//   D          = fp32 in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps
+//                the main loop of tile i+1.
+//   epilogue   = tcgen05.ld -> +bias -> ReLU/LeakyReLU -> InstanceNorm sum/sumsq (warp-shuffle
+//                transposed reduction + one atomic per column per warp) -> bf16/fp32 NHWC store.
+//
+// warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (TMEM lane
+// quadrant = warp & 3).
+#include "common.cuh"
+
+namespace {
+
+struct ConvTcArgs {
+  int n_img, ho, wo, wp;
+  int tw, th, tiles_w, tiles_h;
+  int flat, window;
+  int kw, cchunks, kblocks;
+  int bn, cout, out_c, act, stats, out_f32;
+  int num_m_tiles, num_tiles, stages;
+  uint32_t idesc, a_tx_bytes;
+  const float* bias;
+  float* stats_acc;
+  void* out;
+};
+
+constexpr int kAStageBytes = 16384;  // 128 rows x 128 B
+constexpr int kThreads = 256;
+
+// Sum over the 32 lanes of a warp of v[j] for each j: afterwards lane l holds column l in v[0].
+__device__ __forceinline__ void transposed_warp_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = upper ? v[i + n / 2] : v[i];
+      const float send = upper ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const ConvTcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const int S = p.stages;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * 128u;
+  const uint32_t stage_bytes = kAStageBytes + b_bytes;
+  const uint32_t bar0 = base + S * stage_bytes;           // full[S], empty[S], tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S * stage_bytes + (2 * S + 4) * 8);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * p.bn) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+        const int img = m_tile / tiles_per_img, rem = m_tile % tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
+        const int n0 = n_tile * p.bn;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          int khi, kwi, q;
+          if (p.window) { khi = kb / p.cchunks; q = kb - khi * p.cchunks; kwi = 0; }
+          else { const int per = p.kw * p.cchunks; khi = kb / per; const int r = kb - khi * per;
+                 kwi = r / p.cchunks; q = r - kwi * p.cchunks; }
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
+          mbar_expect_tx(full_bar(stage), p.a_tx_bytes + b_bytes);
+          if (p.flat) tma_load_4d(sa, &tmA, full_bar(stage), q * 64, w0 + khi * p.wp + kwi, 0, img);
+          else        tma_load_4d(sa, &tmA, full_bar(stage), q * 64, w0 + kwi, h0 + khi, img);
+          tma_load_2d(sb, &tmB, full_bar(stage), kb * 64, n0);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.bn);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = umma_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bd = umma_desc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(as));
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+      const int img = m_tile / tiles_per_img, rem = m_tile % tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
+      const int n0 = n_tile * p.bn;
+      int h, w; bool valid;
+      if (p.flat) { const int f = w0 + row; h = f / p.wp; w = f - h * p.wp; valid = (h < p.ho) && (w < p.wo); }
+      else { const int hh = row / p.tw; h = h0 + hh; w = w0 + (row - hh * p.tw);
+             valid = (row < p.tw * p.th) && (h < p.ho) && (w < p.wo); }
+      const size_t pix = (static_cast<size_t>(img) * p.ho + h) * p.wo + w;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.bn);
+      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+        float v[32];
+        if (p.bn - c0 >= 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        } else {  // bn == 16 (mod 32)
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(r[j]); v[j + 16] = 0.f; }
+        }
+        const int col0 = n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          float x = v[j];
+          if (col < p.cout) {
+            if (p.bias) x += __ldg(p.bias + col);
+            x = act_apply(x, p.act);
+          } else x = 0.f;
+          v[j] = x;
+        }
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < p.cout) {
+              float t[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) t[j] = v[g * 8 + j];
+              if (p.out_f32) st8<float>(reinterpret_cast<float*>(p.out) + pix * p.out_c + col, t);
+              else st8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_c + col, t);
+            }
+          }
+        }
+        if (p.stats && col0 < p.cout) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float x = valid ? v[j] : 0.f; s1[j] = x; s2[j] = x * x; }
+          transposed_warp_sum32(s1, lane);
+          transposed_warp_sum32(s2, lane);
+          const int col = col0 + lane;
+          if (col < p.cout) {
+            float* dst = p.stats_acc + (static_cast<size_t>(img) * p.cout + col) * 2;
+            atomicAdd(dst, s1[0]);
+            atomicAdd(dst + 1, s2[0]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------- host side
+static void pick_box(int wo, int ho, int* tw, int* th) {
+  // largest tw*th <= 128 box: full rows when they fit, otherwise the best divisor-free cover
+  if (wo >= 128) { *tw = 128; *th = 1; return; }
+  *tw = wo;
+  int t = 128 / wo;
+  if (t > ho) t = ho;
+  if (t < 1) t = 1;
+  *th = t;
+}
+
+int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+                    float* stats, int out_f32, cudaStream_t stream) {
+  const int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
+  VCG_REQUIRE(d->c % 8 == 0 && d->kwc_pad % 64 == 0 && d->cout_pad % 16 == 0 && d->out_c % 8 == 0,
+              VCG_E_UNSUPPORTED, "conv_tc: unsupported channel geometry c=%d kwc_pad=%d cout_pad=%d cout=%d",
+              d->c, d->kwc_pad, d->cout_pad, d->cout);
+  VCG_REQUIRE(ho > 0 && wo > 0, VCG_E_INVALID, "conv_tc: empty output");
+  const bool window = (d->c % 64) != 0;
+  VCG_REQUIRE(window || d->kwc_pad == d->kw * d->c, VCG_E_INVALID, "conv_tc: kwc_pad mismatch");
+  VCG_REQUIRE(!window || d->kwc_pad == ((d->kw * d->c + 63) / 64) * 64, VCG_E_INVALID, "conv_tc: kwc_pad mismatch (window)");
+
+  ConvTcArgs a{};
+  a.n_img = d->n; a.ho = ho; a.wo = wo; a.wp = d->wp;
+  a.flat = d->flat ? 1 : 0; a.window = window ? 1 : 0;
+  a.kw = d->kw;
+  a.cchunks = window ? d->kwc_pad / 64 : d->c / 64;
+  a.kblocks = d->kh * (d->kwc_pad / 64);
+  if (a.flat) {
+    a.tw = 128; a.th = 1; a.tiles_h = 1;
+    a.tiles_w = (ho * d->wp + 127) / 128;   // rows >= ho are skipped by the epilogue anyway
+    a.a_tx_bytes = 128 * 128;
+  } else {
+    pick_box(wo, ho, &a.tw, &a.th);
+    a.tiles_w = (wo + a.tw - 1) / a.tw;
+    a.tiles_h = (ho + a.th - 1) / a.th;
+    a.a_tx_bytes = static_cast<uint32_t>(a.tw * a.th) * 128u;
+  }
+  a.num_m_tiles = d->n * a.tiles_w * a.tiles_h;
+  const int sms = vcg_num_sms();
+  int bn = d->cout_pad < 256 ? d->cout_pad : 256;
+  if (bn == 256 && static_cast<long long>(a.num_m_tiles) * (d->cout_pad / 256) < sms) bn = 128;
+  if (bn > 64 && (bn % 64) != 0) bn = 64;
+  VCG_REQUIRE(bn % 16 == 0 && bn >= 16, VCG_E_UNSUPPORTED, "conv_tc: bn=%d", bn);
+  a.bn = bn;
+  const int ntn = (d->cout_pad + bn - 1) / bn;
+  a.num_tiles = a.num_m_tiles * ntn;
+  a.cout = d->cout; a.out_c = d->out_c; a.act = d->act; a.stats = (d->stats && stats) ? 1 : 0;
+  a.out_f32 = out_f32;
+  a.bias = bias; a.stats_acc = stats; a.out = y;
+  a.idesc = umma_idesc_bf16(128, bn, 0, 0);
+  const int stage_bytes = kAStageBytes + bn * 128;
+  int stages = (227 * 1024 - 2048) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > a.kblocks) stages = a.kblocks;
+  if (stages < 2) stages = 2;
+  a.stages = stages;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 2048;
+
+  // ---- tensor maps
+  CUtensorMap tmA, tmB;
+  const uint64_t es = 2;
+  const uint64_t pix_stride = static_cast<uint64_t>(d->c) * es;
+  const uint64_t row_stride = static_cast<uint64_t>(d->wp) * pix_stride;
+  const uint64_t img_stride = static_cast<uint64_t>(d->hp) * row_stride;
+  uint64_t dims[4], strides[3];
+  uint32_t box[4];
+  dims[0] = window ? static_cast<uint64_t>(d->kw) * d->c : static_cast<uint64_t>(d->c);
+  if (a.flat) {
+    dims[1] = static_cast<uint64_t>(d->hp) * d->wp - (window ? (d->kw - 1) : 0);
+    dims[2] = 1; dims[3] = d->n;
+    strides[0] = pix_stride; strides[1] = img_stride; strides[2] = img_stride;
+    box[0] = 64; box[1] = 128; box[2] = 1; box[3] = 1;
+  } else {
+    dims[1] = window ? static_cast<uint64_t>(wo) : static_cast<uint64_t>(d->wp);
+    dims[2] = d->hp; dims[3] = d->n;
+    strides[0] = pix_stride; strides[1] = row_stride; strides[2] = img_stride;
+    box[0] = 64; box[1] = a.tw; box[2] = a.th; box[3] = 1;
+  }
+  int rc = vcg_encode_tmap(&tmA, x, 4, dims, strides, box, "conv_tc A");
+  if (rc) return rc;
+  const uint64_t ktot = static_cast<uint64_t>(d->kh) * d->kwc_pad;
+  uint64_t bdims[2] = {ktot, static_cast<uint64_t>(d->cout_pad)};
+  uint64_t bstr[1] = {ktot * es};
+  uint32_t bbox[2] = {64, static_cast<uint32_t>(bn)};
+  rc = vcg_encode_tmap(&tmB, w, 2, bdims, bstr, bbox, "conv_tc B");
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    VCG_REQUIRE(e == cudaSuccess, VCG_E_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+  conv_tc_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, a);
+  VCG_CHECK_LAUNCH("conv_tc_kernel");
+  return VCG_OK;
+}

@@ -1,0 +1,285 @@
+"""Tensor-level wrappers over the C ABI (one function per exported kernel family).
+
+Every function takes pre-allocated torch CUDA tensors and enqueues on the current stream; nothing here
+allocates except where noted, and nothing falls back to PyTorch math."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import lib as L
+
+
+def rup(x, m):
+    return (x + m - 1) // m * m
+
+
+@dataclass(frozen=True)
+class ConvSpec:
+    """Geometry of one reference convolution as executed by the kernels.
+
+    co/ci/kh/kw are the reference OIHW dims (e.g. Networks.py:87 -> (128, 256, 3, 3)); wmap says how the
+    executed input channels map onto them (PixelUnshuffle order / space-to-depth for stride 2)."""
+    co: int
+    ci: int
+    kh: int
+    kw: int
+    wmap: int = L.WMAP_PLAIN
+    c_phys: int = 0          # physical input channels as executed (0 -> derived)
+
+    @property
+    def pkh(self):
+        return self.kh // 2 if self.wmap == L.WMAP_S2D else self.kh
+
+    @property
+    def pkw(self):
+        return self.kw // 2 if self.wmap == L.WMAP_S2D else self.kw
+
+    @property
+    def cin_phys(self):
+        if self.c_phys:
+            return self.c_phys
+        base = self.ci * 4 if self.wmap == L.WMAP_S2D else self.ci
+        return rup(base, 8)
+
+    @property
+    def kwc_pad(self):
+        return rup(self.pkw * self.cin_phys, 64)
+
+    @property
+    def cout_pad(self):
+        return rup(self.co, 16)
+
+    @property
+    def out_c(self):
+        return rup(self.co, 8)
+
+    # data-gradient view: rows = physical input channels, K = (taps, physical output channels)
+    @property
+    def d_rows_pad(self):
+        return rup(self.cin_phys, 16)
+
+    @property
+    def d_kwc_pad(self):
+        return rup(self.pkw * self.out_c, 64)
+
+    def wpack_desc(self, dtype, transpose_flip):
+        return L.WpackDesc(dtype=L.dtype_code(dtype), co=self.co, ci=self.ci, kh=self.kh, kw=self.kw, wmap=self.wmap,
+                           c_phys=self.cin_phys, co_phys=self.out_c,
+                           rows_pad=self.d_rows_pad if transpose_flip else self.cout_pad,
+                           pkh=self.pkh, pkw=self.pkw,
+                           kwc_pad=self.d_kwc_pad if transpose_flip else self.kwc_pad,
+                           transpose_flip=1 if transpose_flip else 0)
+
+    def packed_shape(self, transpose_flip=False):
+        if transpose_flip:
+            return (self.d_rows_pad, self.pkh, self.d_kwc_pad)
+        return (self.cout_pad, self.pkh, self.kwc_pad)
+
+
+def wpack(spec: ConvSpec, w_oihw, out, transpose_flip=False):
+    d = spec.wpack_desc(out.dtype, transpose_flip)
+    assert w_oihw.dtype == torch.float32 and w_oihw.is_contiguous()
+    assert tuple(out.shape) == spec.packed_shape(transpose_flip)
+    L.check(L.load().vcg_wpack(C.byref(d), L.ptr(w_oihw), L.ptr(out), L.stream_ptr()), "vcg_wpack")
+    return out
+
+
+def wunpack_grad(spec: ConvSpec, dw_packed, grad_oihw, accumulate=False):
+    d = spec.wpack_desc(torch.float32, False)
+    assert dw_packed.dtype == torch.float32 and grad_oihw.dtype == torch.float32 and grad_oihw.is_contiguous()
+    L.check(L.load().vcg_wunpack_grad(C.byref(d), L.ptr(dw_packed), L.ptr(grad_oihw), 1 if accumulate else 0,
+                                      L.stream_ptr()), "vcg_wunpack_grad")
+    return grad_oihw
+
+
+def conv_fwd(spec: ConvSpec, x_pad, w_packed, bias, y, stats_acc=None, act=L.ACT_NONE):
+    """y[n,ho,wo,out_c] = act(conv_valid(x_pad, w) + bias); x_pad: [n,hp,wp,cin_phys]."""
+    n, hp, wp, c = x_pad.shape
+    assert c == spec.cin_phys, (c, spec.cin_phys)
+    d = L.ConvDesc(dtype=L.dtype_code(x_pad.dtype), n=n, hp=hp, wp=wp, c=c, kh=spec.pkh, kw=spec.pkw,
+                   kwc_pad=spec.kwc_pad, cout=spec.co, cout_pad=spec.cout_pad, out_c=y.shape[-1], act=act,
+                   stats=1 if stats_acc is not None else 0, flat=0,
+                   out_f32=1 if (y.dtype == torch.float32 and x_pad.dtype != torch.float32) else 0)
+    assert tuple(y.shape[:3]) == (n, hp - spec.pkh + 1, wp - spec.pkw + 1), (y.shape, x_pad.shape)
+    L.check(L.load().vcg_conv_fwd(C.byref(d), L.ptr(x_pad), L.ptr(w_packed), L.ptr(bias), L.ptr(y), L.ptr(stats_acc),
+                                  L.stream_ptr()), "vcg_conv_fwd")
+    return y
+
+
+def conv_dgrad(spec: ConvSpec, dy_pad, w_dgrad, dxp):
+    """dxp[n,hp,wp,cin_phys] = full correlation of the zero-haloed dy with the flipped filter."""
+    n, hd, wd, c = dy_pad.shape
+    assert c == spec.out_c
+    d = L.ConvDesc(dtype=L.dtype_code(dy_pad.dtype), n=n, hp=hd, wp=wd, c=c, kh=spec.pkh, kw=spec.pkw,
+                   kwc_pad=spec.d_kwc_pad, cout=spec.cin_phys, cout_pad=spec.d_rows_pad, out_c=dxp.shape[-1],
+                   act=L.ACT_NONE, stats=0, flat=1, out_f32=0)
+    assert tuple(dxp.shape[:3]) == (n, hd - spec.pkh + 1, wd - spec.pkw + 1), (dxp.shape, dy_pad.shape)
+    L.check(L.load().vcg_conv_fwd(C.byref(d), L.ptr(dy_pad), L.ptr(w_dgrad), None, L.ptr(dxp), None, L.stream_ptr()),
+            "vcg_conv_fwd(dgrad)")
+    return dxp
+
+
+def conv_wgrad(spec: ConvSpec, x_pad, dy_pad, dw_packed):
+    """dw_packed[cout_pad,kh,kwc_pad] += wgrad(x_pad, dy) ; dy_pad carries a zero halo of (k-1)."""
+    n, hp, wp, c = x_pad.shape
+    halo_h, halo_w = spec.pkh - 1, spec.pkw - 1
+    assert halo_h == halo_w
+    d = L.ConvDesc(dtype=L.dtype_code(x_pad.dtype), n=n, hp=hp, wp=wp, c=c, kh=spec.pkh, kw=spec.pkw,
+                   kwc_pad=spec.kwc_pad, cout=spec.co, cout_pad=spec.cout_pad, out_c=dy_pad.shape[-1], act=0, stats=0,
+                   flat=0, out_f32=0)
+    assert dy_pad.shape[1] == hp - spec.pkh + 1 + 2 * halo_h
+    L.check(L.load().vcg_conv_wgrad(C.byref(d), L.ptr(x_pad), L.ptr(dy_pad), halo_h, dy_pad.shape[-1], L.ptr(dw_packed),
+                                    L.stream_ptr()), "vcg_conv_wgrad")
+    return dw_packed
+
+
+def in_stats(y, c, mean_rstd):
+    """mean/rstd [n,c,2] of a dense NHWC tensor (fp64 accumulation).  mean_rstd: float32 [n*c*2*3]."""
+    n, h, w, cp = y.shape
+    assert mean_rstd.numel() >= n * c * 6
+    L.check(L.load().vcg_in_stats(L.dtype_code(y.dtype), L.ptr(y), n, h * w, c, cp, L.ptr(mean_rstd), L.stream_ptr()),
+            "vcg_in_stats")
+    return mean_rstd
+
+
+def in_finalize(sums, nc, hw, mean_rstd):
+    L.check(L.load().vcg_in_finalize(L.ptr(sums), nc, hw, L.ptr(mean_rstd), L.stream_ptr()), "vcg_in_finalize")
+    return mean_rstd
+
+
+def xform_dst_shape(n, h, w, c, mode, pad, dst_c=None):
+    if mode == L.MODE_PLAIN:
+        hd, wd, cd = h + 2 * pad, w + 2 * pad, c
+    elif mode == L.MODE_SHUFFLE:
+        hd, wd, cd = 2 * h + 2 * pad, 2 * w + 2 * pad, c // 4
+    elif mode == L.MODE_UNSHUFFLE:
+        hd, wd, cd = h // 2 + 2 * pad, w // 2 + 2 * pad, c * 4
+    else:
+        hd, wd, cd = (h + 2 * pad) // 2, (w + 2 * pad) // 2, c * 4
+    return (n, hd, wd, dst_c or rup(cd, 8))
+
+
+def xform_fwd(src, c, dst, mode, pad, mean_rstd=None, act=L.ACT_NONE, residual=None, res_off=0):
+    n, h, w, src_c = src.shape
+    d = L.XformDesc(dtype=L.dtype_code(src.dtype), n=n, h=h, w=w, c=c, src_c=src_c,
+                    norm=1 if mean_rstd is not None else 0, act=act, mode=mode, pad=pad, dst_c=dst.shape[-1],
+                    res_hp=residual.shape[1] if residual is not None else 0,
+                    res_wp=residual.shape[2] if residual is not None else 0,
+                    res_c=residual.shape[3] if residual is not None else 0, res_off=res_off)
+    assert tuple(dst.shape) == xform_dst_shape(n, h, w, c, mode, pad, dst.shape[-1]), (dst.shape, src.shape, mode, pad)
+    L.check(L.load().vcg_xform_fwd(C.byref(d), L.ptr(src), L.ptr(mean_rstd), L.ptr(residual), L.ptr(dst), L.stream_ptr()),
+            "vcg_xform_fwd")
+    return dst
+
+
+def _xb_desc(y_like_dtype, n, h, w, c, y_c, norm, act, pre_act, dy, dy_halo, nsrc):
+    return L.XbwdDesc(dtype=L.dtype_code(y_like_dtype), n=n, h=h, w=w, c=c, y_c=y_c, norm=1 if norm else 0, act=act,
+                      pre_act=pre_act, dy_halo=dy_halo, dy_c=dy.shape[-1], nsrc=nsrc)
+
+
+def xform_bwd_gather(srcs, y, n, h, w, c, dy, dy_halo, mean_rstd=None, act=L.ACT_NONE, pre_act=L.ACT_NONE,
+                     gsums=None, dbias=None):
+    """srcs: list of (dxp tensor, mode, pad).  Writes g into the interior of dy (+ sums for phase 2)."""
+    arr = (L.GSrc * max(1, len(srcs)))()
+    for i, (t, mode, pad) in enumerate(srcs):
+        arr[i].dxp = t.data_ptr()
+        arr[i].mode, arr[i].pad, arr[i].c_pitch = mode, pad, t.shape[-1]
+    norm = mean_rstd is not None
+    d = _xb_desc(dy.dtype, n, h, w, c, y.shape[-1] if y is not None else 8, norm, act, pre_act, dy, dy_halo, len(srcs))
+    L.check(L.load().vcg_xform_bwd_gather(C.byref(d), arr, L.ptr(y), L.ptr(mean_rstd), L.ptr(dy), L.ptr(gsums),
+                                          L.ptr(dbias), L.stream_ptr()), "vcg_xform_bwd_gather")
+    return dy
+
+
+def xform_bwd_norm(y, n, h, w, c, dy, dy_halo, mean_rstd, gsums, pre_act=L.ACT_NONE, dbias=None):
+    d = _xb_desc(dy.dtype, n, h, w, c, y.shape[-1], True, L.ACT_NONE, pre_act, dy, dy_halo, 0)
+    L.check(L.load().vcg_xform_bwd_norm(C.byref(d), L.ptr(y), L.ptr(mean_rstd), L.ptr(gsums), L.ptr(dy), L.ptr(dbias),
+                                        L.stream_ptr()), "vcg_xform_bwd_norm")
+    return dy
+
+
+def pack_nchw(src, dst, halo=0):
+    n, c, h, w = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    assert tuple(dst.shape[:3]) == (n, h + 2 * halo, w + 2 * halo)
+    L.check(L.load().vcg_pack_nchw(L.dtype_code(dst.dtype), L.ptr(src), n, c, h, w, L.ptr(dst), dst.shape[-1], halo,
+                                   L.stream_ptr()), "vcg_pack_nchw")
+    return dst
+
+
+def unpack_nchw(src, c, dst, c_off=0):
+    n, h, w, src_c = src.shape
+    assert dst.dtype == torch.float32 and dst.is_contiguous() and tuple(dst.shape) == (n, c, h, w)
+    base = C.c_void_p(src.data_ptr() + c_off * src.element_size())
+    L.check(L.load().vcg_unpack_nchw(L.dtype_code(src.dtype), base, src_c, n, c, h, w, L.ptr(dst), L.stream_ptr()),
+            "vcg_unpack_nchw")
+    return dst
+
+
+def zero_(t):
+    L.check(L.load().vcg_zero(L.ptr(t), t.numel() * t.element_size(), L.stream_ptr()), "vcg_zero")
+    return t
+
+
+def l1_fwd_bwd(a, b, out_sum, grad=None, scale=0.0):
+    L.check(L.load().vcg_l1_fwd_bwd(L.ptr(a), L.ptr(b), a.numel(), scale, L.ptr(out_sum), L.ptr(grad), L.stream_ptr()),
+            "vcg_l1_fwd_bwd")
+
+
+def mse_const_fwd_bwd(d, target, out_sum, grad=None, scale=0.0):
+    L.check(L.load().vcg_mse_const_fwd_bwd(L.ptr(d), d.numel(), float(target), scale, L.ptr(out_sum), L.ptr(grad),
+                                           L.stream_ptr()), "vcg_mse_const_fwd_bwd")
+
+
+def kl_fwd_bwd(mu, lv, out_sum, gmu=None, glv=None, scale=0.0):
+    L.check(L.load().vcg_kl_fwd_bwd(L.ptr(mu), L.ptr(lv), mu.numel(), scale, L.ptr(out_sum), L.ptr(gmu), L.ptr(glv),
+                                    L.stream_ptr()), "vcg_kl_fwd_bwd")
+
+
+def _off(t, c_off):
+    return C.c_void_p(t.data_ptr() + c_off * t.element_size())
+
+
+def reparam_fwd(mu_src, mu_off, lv_src, lv_off, eps, c, z, mu_out, lv_out, kl_sum=None):
+    n, h, w, _ = mu_src.shape
+    L.check(L.load().vcg_reparam_fwd(L.dtype_code(mu_src.dtype), _off(mu_src, mu_off), mu_src.shape[-1],
+                                     _off(lv_src, lv_off), lv_src.shape[-1], L.ptr(eps), n, h * w, c, L.ptr(z),
+                                     L.ptr(mu_out), L.ptr(lv_out), L.ptr(kl_sum), L.stream_ptr()), "vcg_reparam_fwd")
+
+
+def reparam_bwd(mu_src, mu_off, lv_src, lv_off, eps, dz, c, dmu, dlv, gmu_ext=None, glv_ext=None, kl_scale=0.0):
+    n, h, w, _ = mu_src.shape
+    L.check(L.load().vcg_reparam_bwd(L.dtype_code(mu_src.dtype), _off(mu_src, mu_off), mu_src.shape[-1],
+                                     _off(lv_src, lv_off), lv_src.shape[-1], L.ptr(eps), L.ptr(dz), dz.shape[-1],
+                                     L.ptr(gmu_ext), L.ptr(glv_ext), kl_scale, n, h * w, c, L.ptr(dmu), dmu.shape[-1],
+                                     L.ptr(dlv), dlv.shape[-1], L.stream_ptr()), "vcg_reparam_bwd")
+
+
+def dhead_fwd(x, w_khwc, bias, score, wnorm2):
+    n = x.shape[0]
+    k = x[0].numel()
+    L.check(L.load().vcg_dhead_fwd(L.dtype_code(x.dtype), L.ptr(x), L.ptr(w_khwc), L.ptr(bias), n, k, L.ptr(score),
+                                   L.ptr(wnorm2), L.stream_ptr()), "vcg_dhead_fwd")
+
+
+def dhead_bwd(x, w_khwc, wnorm2, gscore, dx, dw, dbias, scratch):
+    n = x.shape[0]
+    k = x[0].numel()
+    L.check(L.load().vcg_dhead_bwd(L.dtype_code(x.dtype), L.ptr(x), L.ptr(w_khwc), L.ptr(wnorm2), L.ptr(gscore), n, k,
+                                   L.ptr(dx), L.ptr(dw), L.ptr(dbias), L.ptr(scratch), L.stream_ptr()), "vcg_dhead_bwd")
+
+
+def adam_multi(chunks_dev, nchunks, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    bc1 = 1.0 - beta1 ** step
+    bc2_sqrt = (1.0 - beta2 ** step) ** 0.5
+    L.check(L.load().vcg_adam_multi(L.ptr(chunks_dev), nchunks, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale,
+                                    L.stream_ptr()), "vcg_adam_multi")
+
+
+def probe_tmap(base_tensor, dims, strides_bytes, box):
+    r = len(dims)
+    return L.load().vcg_probe_tmap(L.ptr(base_tensor), r, (C.c_uint64 * r)(*dims), (C.c_uint64 * max(1, r - 1))(*strides_bytes),
+                                   (C.c_uint32 * r)(*box))
