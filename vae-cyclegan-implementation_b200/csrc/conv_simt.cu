@@ -77,8 +77,9 @@ conv_fwd_simt_kernel(const T* __restrict__ x, const T* __restrict__ w, const flo
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int co = n0 + tx * 4 + j;
-      if (co >= p.cout) continue;
-      float v = acc[i][j] + (bias ? bias[co] : 0.f);
+      if (co >= p.out_c) continue;
+      // pad channels [cout, out_c) are written as zeros, like the tensor-core epilogue does
+      float v = co < p.cout ? acc[i][j] + (bias ? bias[co] : 0.f) : 0.f;
       v = act_apply(v, p.act);
       if (p.out_f32) reinterpret_cast<float*>(y)[pix * p.out_c + co] = v;
       else Elem<T>::st(reinterpret_cast<T*>(y) + pix * p.out_c + co, v);
