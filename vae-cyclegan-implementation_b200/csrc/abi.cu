@@ -97,7 +97,11 @@ extern "C" int vcg_conv_wgrad(const vcg_conv_desc* d, const void* x, const void*
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VCG_REQUIRE(d && x && dy && dw, VCG_E_INVALID, "conv_wgrad: null argument");
   VCG_REQUIRE(d->dtype == VCG_F32 || d->dtype == VCG_BF16, VCG_E_UNSUPPORTED, "conv_wgrad: dtype %d", d->dtype);
-  // degenerate M (cout < 16, i.e. the 64->3 output convolution) stays on the SIMT kernel
-  if (d->dtype == VCG_F32 || force_simt() || d->cout < 16) return vcg_conv_wgrad_simt(d, d->dtype, x, dy, dy_halo, dy_c, dw, stream);
+  // degenerate M (cout < 16, i.e. the 64->3 output convolution) and feature maps that cannot be cut
+  // into 64-pixel TMA boxes (inputs smaller than 256x256) stay on the SIMT kernel
+  const int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
+  const bool tileable = wo >= 64 ? (wo % 64 == 0) : (64 % wo == 0 && ho % (64 / wo) == 0);
+  if (d->dtype == VCG_F32 || force_simt() || d->cout < 16 || !tileable)
+    return vcg_conv_wgrad_simt(d, d->dtype, x, dy, dy_halo, dy_c, dw, stream);
   return vcg_conv_wgrad_tc(d, x, dy, dy_halo, dy_c, dw, stream);
 }

@@ -27,7 +27,7 @@ conv_fwd_simt_kernel(const T* __restrict__ x, const T* __restrict__ w, const flo
   const long long m0 = static_cast<long long>(blockIdx.x) * TM;
   const int n0 = blockIdx.y * TN;
   const int tx = tid & 15, ty = tid >> 4;   // 16 x 16 threads, 4x4 outputs each
-  float acc[4][4] = {};
+  double acc[4][4] = {};   // fp64 accumulation: the parity mode must not add summation noise of its own
   const int kwc = p.kw * p.c;
   // loader mapping: 256 threads load 64 rows x 16 k -> 4 elements each (row = tid/4, k = (tid%4)*4..)
   const int lrow = tid >> 2, lk = (tid & 3) * 4;
@@ -59,13 +59,13 @@ conv_fwd_simt_kernel(const T* __restrict__ x, const T* __restrict__ w, const flo
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < TK; ++k) {
-        float a[4], b[4];
+        double a[4], b[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
       }
       __syncthreads();
     }
@@ -79,7 +79,7 @@ conv_fwd_simt_kernel(const T* __restrict__ x, const T* __restrict__ w, const flo
       const int co = n0 + tx * 4 + j;
       if (co >= p.out_c) continue;
       // pad channels [cout, out_c) are written as zeros, like the tensor-core epilogue does
-      float v = co < p.cout ? acc[i][j] + (bias ? bias[co] : 0.f) : 0.f;
+      float v = co < p.cout ? static_cast<float>(acc[i][j] + (bias ? static_cast<double>(bias[co]) : 0.0)) : 0.f;
       v = act_apply(v, p.act);
       if (p.out_f32) reinterpret_cast<float*>(y)[pix * p.out_c + co] = v;
       else Elem<T>::st(reinterpret_cast<T*>(y) + pix * p.out_c + co, v);
@@ -102,7 +102,7 @@ conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, float*
   const int j0 = blockIdx.x * TN, co0 = blockIdx.y * TM;
   const int khi = blockIdx.z % p.kh, split = blockIdx.z / p.kh;
   const int tx = tid & 15, ty = tid >> 4;
-  float acc[4][4] = {};
+  double acc[4][4] = {};   // fp64 accumulation: the parity mode must not add summation noise of its own
   const int kwc = p.kw * p.c;
   const long long pbeg = static_cast<long long>(split) * p.pix_per_split;
   long long pend = pbeg + p.pix_per_split;
@@ -129,13 +129,13 @@ conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, float*
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < TK; ++k) {
-      float a[4], b[4];
+      double a[4], b[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -147,7 +147,7 @@ conv_wgrad_simt_kernel(const T* __restrict__ x, const T* __restrict__ dy, float*
     for (int j = 0; j < 4; ++j) {
       const int jj = j0 + tx * 4 + j;
       if (jj >= kwc) continue;
-      atomicAdd(dw + (static_cast<long long>(co) * p.kh + khi) * p.kwc_pad + jj, acc[i][j]);
+      atomicAdd(dw + (static_cast<long long>(co) * p.kh + khi) * p.kwc_pad + jj, static_cast<float>(acc[i][j]));
     }
   }
 }

@@ -16,6 +16,35 @@ def rup(x, m):
     return (x + m - 1) // m * m
 
 
+class _Prof:
+    """Optional CUDA-event instrumentation of the conv GEMM launches (bench.py's roofline leg)."""
+    records = None
+
+
+def prof_begin():
+    _Prof.records = []
+
+
+def prof_end():
+    r, _Prof.records = _Prof.records, None
+    return r
+
+
+def _rec(kind, flops):
+    if _Prof.records is None:
+        return None
+    s = torch.cuda.Event(enable_timing=True)
+    s.record()
+    return (kind, flops, s)
+
+
+def _rec_end(tok):
+    if tok is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        _Prof.records.append((*tok, e))
+
+
 @dataclass(frozen=True)
 class ConvSpec:
     """Geometry of one reference convolution as executed by the kernels.
@@ -73,6 +102,11 @@ class ConvSpec:
                            kwc_pad=self.d_kwc_pad if transpose_flip else self.kwc_pad,
                            transpose_flip=1 if transpose_flip else 0)
 
+    def flops(self, n, ho, wo):
+        """algorithmic FLOPs of one pass (forward, data-gradient or weight-gradient): 2*M*N*K with the
+        reference's logical dims"""
+        return 2.0 * n * ho * wo * self.co * self.ci * self.kh * self.kw
+
     def packed_shape(self, transpose_flip=False):
         if transpose_flip:
             return (self.d_rows_pad, self.pkh, self.d_kwc_pad)
@@ -104,8 +138,10 @@ def conv_fwd(spec: ConvSpec, x_pad, w_packed, bias, y, stats_acc=None, act=L.ACT
                    stats=1 if stats_acc is not None else 0, flat=0,
                    out_f32=1 if (y.dtype == torch.float32 and x_pad.dtype != torch.float32) else 0)
     assert tuple(y.shape[:3]) == (n, hp - spec.pkh + 1, wp - spec.pkw + 1), (y.shape, x_pad.shape)
+    tok = _rec("conv_fwd", spec.flops(n, y.shape[1], y.shape[2]))
     L.check(L.load().vcg_conv_fwd(C.byref(d), L.ptr(x_pad), L.ptr(w_packed), L.ptr(bias), L.ptr(y), L.ptr(stats_acc),
                                   L.stream_ptr()), "vcg_conv_fwd")
+    _rec_end(tok)
     return y
 
 
@@ -117,8 +153,10 @@ def conv_dgrad(spec: ConvSpec, dy_pad, w_dgrad, dxp):
                    kwc_pad=spec.d_kwc_pad, cout=spec.cin_phys, cout_pad=spec.d_rows_pad, out_c=dxp.shape[-1],
                    act=L.ACT_NONE, stats=0, flat=1, out_f32=0)
     assert tuple(dxp.shape[:3]) == (n, hd - spec.pkh + 1, wd - spec.pkw + 1), (dxp.shape, dy_pad.shape)
+    tok = _rec("conv_dgrad", spec.flops(n, hd - 2 * (spec.pkh - 1), wd - 2 * (spec.pkw - 1)))
     L.check(L.load().vcg_conv_fwd(C.byref(d), L.ptr(dy_pad), L.ptr(w_dgrad), None, L.ptr(dxp), None, L.stream_ptr()),
             "vcg_conv_fwd(dgrad)")
+    _rec_end(tok)
     return dxp
 
 
@@ -131,8 +169,10 @@ def conv_wgrad(spec: ConvSpec, x_pad, dy_pad, dw_packed):
                    kwc_pad=spec.kwc_pad, cout=spec.co, cout_pad=spec.cout_pad, out_c=dy_pad.shape[-1], act=0, stats=0,
                    flat=0, out_f32=0)
     assert dy_pad.shape[1] == hp - spec.pkh + 1 + 2 * halo_h
+    tok = _rec("conv_wgrad", spec.flops(n, hp - spec.pkh + 1, wp - spec.pkw + 1))
     L.check(L.load().vcg_conv_wgrad(C.byref(d), L.ptr(x_pad), L.ptr(dy_pad), halo_h, dy_pad.shape[-1], L.ptr(dw_packed),
                                     L.stream_ptr()), "vcg_conv_wgrad")
+    _rec_end(tok)
     return dw_packed
 
 

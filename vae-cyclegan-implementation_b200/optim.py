@@ -1,0 +1,110 @@
+"""FusedAdam: torch.optim.Adam's interface (param_groups, state_dict()/load_state_dict() with the
+same keys -- exp_avg, exp_avg_sq, step -- so reference checkpoints interoperate, Networks.py:315-328,
+utils.py:22,47) with the update done by ONE multi-tensor kernel launch (csrc/adam.cu) instead of the
+foreach kernel sequence of torch/optim/adam.py:457-547.
+
+Gradients live in one flat fp32 buffer (``.grad`` tensors are views into it): zero_grad() is a single
+fill, and data-parallel training all-reduces the flat buffer in buckets (dist.py)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as L
+from . import ops
+
+CHUNK = 65536
+
+
+class FusedAdam(torch.optim.Adam):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, flat_grads=True):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, foreach=False)
+        self._flat_grads = flat_grads
+        self._flat = None
+        self._table = None
+        self._table_key = None
+        self.grad_scale = 1.0       # data-parallel averaging folded into the update (dist.py sets 1/world)
+        self.pre_step_hook = None   # dist.py: all-reduce of the flat gradient buffer
+
+    # ---- flat gradient buffer -------------------------------------------------------------
+    def _params(self):
+        return [p for g in self.param_groups for p in g["params"] if p.requires_grad]
+
+    def flat_grad(self):
+        """Allocate (once) the flat gradient buffer and point every .grad into it."""
+        ps = self._params()
+        if self._flat is None or self._flat.device != ps[0].device:
+            total = sum((p.numel() + 3) // 4 * 4 for p in ps)     # keep every view 16-byte aligned
+            self._flat = torch.zeros(total, dtype=torch.float32, device=ps[0].device)
+            off = 0
+            for p in ps:
+                p.grad = self._flat[off:off + p.numel()].view_as(p)
+                off += (p.numel() + 3) // 4 * 4
+        return self._flat
+
+    def zero_grad(self, set_to_none=True):
+        if not self._flat_grads or not self._params() or not self._params()[0].is_cuda:
+            return super().zero_grad(set_to_none)
+        flat = self.flat_grad()
+        ops.zero_(flat)
+        off = 0
+        for p in self._params():       # re-attach views dropped by an external zero_grad(set_to_none=True)
+            if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + 4 * off:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+            off += (p.numel() + 3) // 4 * 4
+
+    # ---- the update ---------------------------------------------------------------------------
+    def _build_table(self, items):
+        rows = []
+        for p, g, m, v in items:
+            n = p.numel()
+            for o in range(0, n, CHUNK):
+                rows.append((p.data_ptr() + 4 * o, g.data_ptr() + 4 * o, m.data_ptr() + 4 * o, v.data_ptr() + 4 * o,
+                             min(CHUNK, n - o)))
+        arr = (L.AdamChunk * len(rows))()
+        for i, r in enumerate(rows):
+            arr[i].p, arr[i].g, arr[i].m, arr[i].v, arr[i].numel = r
+        host = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy())
+        return host.to(items[0][0].device), len(rows)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        if self.pre_step_hook is not None:
+            self.pre_step_hook(self)
+        for group in self.param_groups:
+            beta1, beta2 = group["betas"]
+            items, steps = [], []
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda:
+                    raise RuntimeError("FusedAdam: CUDA parameters required (no CPU fallback)")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                g = p.grad
+                if not g.is_contiguous() or g.dtype != torch.float32:
+                    raise RuntimeError("FusedAdam: gradients must be contiguous fp32")
+                items.append((p, g, st["exp_avg"], st["exp_avg_sq"]))
+                steps.append(st["step"])
+            if not items:
+                continue
+            key = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()) for p, g, m, v in items)
+            if key != self._table_key or len(self.param_groups) > 1:
+                self._table = self._build_table(items)
+                self._table_key = key
+            for s in steps:
+                s += 1
+            stepno = int(steps[0].item())
+            if any(int(s.item()) != stepno for s in steps[1:]):
+                raise RuntimeError("FusedAdam: parameters of one group must share the step count")
+            table, nchunks = self._table
+            ops.adam_multi(table, nchunks, group["lr"], beta1, beta2, group["eps"], stepno, self.grad_scale)
+            for p, _, _, _ in items:        # the kernel wrote p behind autograd's back: invalidate packed copies
+                p._vcg_epoch = getattr(p, "_vcg_epoch", 0) + 1
+        return loss

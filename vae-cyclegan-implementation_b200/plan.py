@@ -1,0 +1,461 @@
+"""Network plans: the reference's modules compiled to a DAG of kernel launches.
+
+A *plan* is built by the modules of Networks.py emitting nodes into a PlanBuilder (conv layers with
+their input transform, the VAE bottleneck, the discriminator head).  `run_forward` executes it on the
+current CUDA stream through the C ABI only (ops.py); `run_backward` executes the exact adjoint in
+reverse order: for every activation the gradient is *gathered* from the padded-input gradients of its
+consumers (halo folded, pixel shuffle inverted), pushed through the activation / InstanceNorm
+derivative into a zero-haloed dY, then the weight-gradient and data-gradient GEMMs run.
+
+Activations ("Act") are what a reference module returns (Networks.py:57-149): the raw conv output
+plus a *pending* normalisation / activation / residual that is applied by the consumer's input
+transform, so no normalised tensor is ever written to HBM on its own."""
+from __future__ import annotations
+
+import torch
+
+from . import lib as L
+from . import ops
+
+_STATE = {"dtype": torch.bfloat16, "input_grads": True}
+
+
+def set_precision(mode):
+    """'bf16' (tcgen05 tensor-core kernels, fp32 accumulate) or 'fp32' (FFMA parity kernels)."""
+    _STATE["dtype"] = {"bf16": torch.bfloat16, "fp32": torch.float32}[mode]
+
+
+def get_precision():
+    return "bf16" if _STATE["dtype"] == torch.bfloat16 else "fp32"
+
+
+class no_wgrad:
+    """Context manager: skip weight gradients of the given modules (the reference computes the
+    discriminators' weight gradients during the generator backward and then discards them,
+    Networks.py:2020-2025)."""
+
+    def __init__(self, *modules):
+        self.params = [p for m in modules for p in m.parameters()]
+
+    def __enter__(self):
+        self.prev = [getattr(p, "_vcg_skip_wgrad", False) for p in self.params]
+        for p in self.params:
+            p._vcg_skip_wgrad = True
+
+    def __exit__(self, *exc):
+        for p, v in zip(self.params, self.prev):
+            p._vcg_skip_wgrad = v
+
+
+def _wants_grad(p):
+    return p.requires_grad and not getattr(p, "_vcg_skip_wgrad", False)
+
+
+# ----------------------------------------------------------------------------- plan description
+class Act:
+    """A finished activation: raw tensor (conv output / external / z) + pending norm, act, residual."""
+    _next = 0
+
+    def __init__(self, c, c_log, h, w, producer=None, norm=False, act=L.ACT_NONE, res=None, kind="conv"):
+        self.id = Act._next
+        Act._next += 1
+        self.c, self.c_log, self.h, self.w = c, c_log, h, w
+        self.producer, self.norm, self.act, self.res, self.kind = producer, norm, act, res, kind
+        self.consumers = []      # nodes reading this act
+        self.passthrough = []    # acts that add this act as their residual
+        if res is not None:
+            res.passthrough.append(self)
+
+
+class ConvNode:
+    def __init__(self, holder, spec, inp, mode, pad, pre_act):
+        self.holder, self.spec, self.inp, self.mode, self.pad, self.pre_act = holder, spec, inp, mode, pad, pre_act
+        self.out_acts = []
+
+
+class ReparamNode:
+    def __init__(self, mu, lv, z):
+        self.mu, self.lv, self.z = mu, lv, z
+
+
+class HeadNode:
+    def __init__(self, holder, inp):
+        self.holder, self.inp = holder, inp
+
+
+class PlanBuilder:
+    def __init__(self, n):
+        self.n = n
+        self.nodes = []
+        self.inputs = []
+        self.outputs = []     # (act, kind) kind in {"image", "mu", "logvar", "score"}
+
+    def input(self, c_log, h, w):
+        a = Act(ops.rup(c_log, 8), c_log, h, w, kind="ext")
+        self.inputs.append(a)
+        return a
+
+    def conv(self, holder, inp, mode=L.MODE_PLAIN, pad=1, pre_act=L.ACT_NONE, norm=False, act=L.ACT_NONE):
+        co, ci, kh, kw = holder.weight.shape
+        if mode == L.MODE_PLAIN:
+            wmap, c_phys, hs, ws = L.WMAP_PLAIN, inp.c, inp.h, inp.w
+        elif mode == L.MODE_SHUFFLE:
+            wmap, c_phys, hs, ws = L.WMAP_PLAIN, inp.c // 4, inp.h * 2, inp.w * 2
+        elif mode == L.MODE_UNSHUFFLE:
+            wmap, c_phys, hs, ws = L.WMAP_UNSHUFFLE, inp.c * 4, inp.h // 2, inp.w // 2
+        else:
+            wmap, c_phys, hs, ws = L.WMAP_S2D, inp.c * 4, None, None
+        spec = ops.ConvSpec(co, ci, kh, kw, wmap, c_phys)
+        if mode == L.MODE_PAD_S2D:
+            ho, wo = (inp.h + 2 * pad) // 2 - spec.pkh + 1, (inp.w + 2 * pad) // 2 - spec.pkw + 1
+        else:
+            ho, wo = hs + 2 * pad - kh + 1, ws + 2 * pad - kw + 1
+        node = ConvNode(holder, spec, inp, mode, pad, pre_act)
+        out = Act(spec.out_c, co, ho, wo, producer=node, norm=norm, act=act)
+        node.out_acts.append(out)
+        inp.consumers.append(node)
+        self.nodes.append(node)
+        return out
+
+    def residual(self, main, res):
+        """main + res, where main is a conv output with its pending norm (R block, Networks.py:108-116)."""
+        a = Act(main.c, main.c_log, main.h, main.w, producer=main.producer, norm=main.norm, act=main.act, res=res)
+        main.producer.out_acts.append(a)
+        return a
+
+    def reparam(self, mu, lv):
+        z = Act(mu.c, mu.c_log, mu.h, mu.w, kind="z")
+        node = ReparamNode(mu, lv, z)
+        z.producer = node
+        mu.consumers.append(node)
+        lv.consumers.append(node)
+        self.nodes.append(node)
+        return z
+
+    def head(self, holder, inp):
+        node = HeadNode(holder, inp)
+        inp.consumers.append(node)
+        self.nodes.append(node)
+        self.outputs.append((node, "score"))
+        return node
+
+    def output(self, act, kind="image"):
+        self.outputs.append((act, kind))
+
+
+# ----------------------------------------------------------------------------- parameter caches
+class PackedConv:
+    """Kernel-layout copies of one conv's master weight, refreshed when the master changes
+    (tensor._version is bumped by the optimiser's in-place update and by load_state_dict)."""
+
+    def __init__(self, holder, spec):
+        self.holder, self.spec = holder, spec
+        self.key = None
+        self.wk = self.wkT = self.dw = self.dbias = None
+
+    def refresh(self, dtype):
+        w = self.holder.weight
+        key = (w._version, getattr(w, "_vcg_epoch", 0), w.data_ptr(), dtype, w.device)
+        if key != self.key:
+            wc = w.detach()
+            if not wc.is_contiguous():
+                wc = wc.contiguous()
+            if self.wk is None or self.wk.dtype != dtype or self.wk.device != w.device:
+                self.wk = torch.empty(self.spec.packed_shape(False), dtype=dtype, device=w.device)
+                self.wkT = torch.empty(self.spec.packed_shape(True), dtype=dtype, device=w.device)
+            ops.wpack(self.spec, wc, self.wk, False)
+            ops.wpack(self.spec, wc, self.wkT, True)
+            self.key = key
+        return self
+
+    def grad_buffers(self):
+        dev = self.holder.weight.device
+        if self.dw is None or self.dw.device != dev:
+            self.dw = torch.empty(self.spec.packed_shape(False), dtype=torch.float32, device=dev)
+            self.dbias = torch.empty(ops.rup(self.spec.co, 8), dtype=torch.float32, device=dev)
+        return self.dw, self.dbias
+
+
+def packed_for(holder, spec):
+    cache = holder.__dict__.setdefault("_vcg_packed", {})
+    pc = cache.get(spec)
+    if pc is None:
+        pc = cache[spec] = PackedConv(holder, spec)
+    return pc
+
+
+def _accumulate_grad(param, fn_write):
+    """fn_write(grad_tensor, accumulate: bool) fills/accumulates param.grad in place (no autograd
+    AccumulateGrad round trip: the wgrad GEMM result is unpacked straight into .grad)."""
+    if param.grad is None:
+        param.grad = torch.empty_like(param, memory_format=torch.contiguous_format)
+        fn_write(param.grad, False)
+    else:
+        fn_write(param.grad, True)
+
+
+# ----------------------------------------------------------------------------- execution
+class Run:
+    """Tensors of one forward execution that the backward needs (saved activations)."""
+
+    def __init__(self):
+        self.Y, self.MR, self.XP = {}, {}, {}
+        self.xp_of_node = {}
+        self.plain = {}        # act id -> (padded tensor, pad): where a residual can be read from
+        self.ext = {}          # act id -> dense NHWC tensor (external inputs, z)
+        self.reparam = {}      # node -> (eps,)
+        self.head = {}         # node -> (x dense, w_khwc, wnorm2)
+
+
+class Plan:
+    def __init__(self, builder):
+        self.n = builder.n
+        self.nodes, self.inputs, self.outputs = builder.nodes, builder.inputs, builder.outputs
+
+    # ------------------------------------------------------------------ forward
+    def _raw(self, run, act):
+        return run.Y[act.producer] if act.kind == "conv" else run.ext[act.id]
+
+    def _materialize(self, run, act, mode, pad, dtype):
+        key = (act.id, mode, pad)
+        xp = run.XP.get(key)
+        if xp is None:
+            src = self._raw(run, act)
+            shape = ops.xform_dst_shape(self.n, act.h, act.w, act.c, mode, pad)
+            xp = torch.empty(shape, dtype=dtype, device=src.device)
+            mr = run.MR[act.producer] if act.norm else None
+            resbuf, off = run.plain[act.res.id] if act.res is not None else (None, 0)
+            ops.xform_fwd(src, act.c, xp, mode, pad, mr, act.act, resbuf, off)
+            run.XP[key] = xp
+            if mode == L.MODE_PLAIN and act.id not in run.plain:
+                run.plain[act.id] = (xp, pad)
+        return xp
+
+    def run_forward(self, inputs, eps_list=(), keep=True):
+        """inputs: NCHW fp32 CUDA tensors (one per plan input).  Returns (outputs, run)."""
+        dtype = _STATE["dtype"]
+        run = Run()
+        n = self.n
+        dev = inputs[0].device
+        for a, x in zip(self.inputs, inputs):
+            x = x.detach()
+            if x.dtype != torch.float32 or not x.is_contiguous():
+                x = x.float().contiguous()
+            t = torch.empty(n, a.h, a.w, a.c, dtype=dtype, device=dev)
+            ops.pack_nchw(x, t)
+            run.ext[a.id] = t
+        eps_iter = iter(eps_list)
+        outs = []
+        out_nodes = {id(o[0]): o[1] for o in self.outputs}
+        for node in self.nodes:
+            if isinstance(node, ConvNode):
+                xp = self._materialize(run, node.inp, node.mode, node.pad, dtype)
+                run.xp_of_node[node] = xp
+                pc = packed_for(node.holder, node.spec).refresh(dtype)
+                a0 = node.out_acts[0]
+                # the final image layer (conv -> Identity, no norm, Networks.py:192) is stored in fp32
+                final_image = (dtype != torch.float32 and len(node.out_acts) == 1 and id(a0) in out_nodes
+                               and not a0.consumers and not a0.norm and a0.act == L.ACT_NONE
+                               and node.pre_act == L.ACT_NONE)
+                y = torch.empty(n, a0.h, a0.w, node.spec.out_c, dtype=torch.float32 if final_image else dtype, device=dev)
+                bias = node.holder.bias.detach()
+                if a0.norm and dtype == torch.bfloat16:
+                    acc = ops.zero_(torch.empty(n * node.spec.co * 2, dtype=torch.float32, device=dev))
+                    ops.conv_fwd(node.spec, xp, pc.wk, bias, y, acc, node.pre_act)
+                    run.MR[node] = ops.in_finalize(acc, n * node.spec.co, a0.h * a0.w, torch.empty_like(acc))
+                else:
+                    ops.conv_fwd(node.spec, xp, pc.wk, bias, y, None, node.pre_act)
+                    if a0.norm:
+                        mr = torch.empty(n * node.spec.co * 6, dtype=torch.float32, device=dev)
+                        run.MR[node] = ops.in_stats(y, node.spec.co, mr)
+                run.Y[node] = y
+            elif isinstance(node, ReparamNode):
+                eps = next(eps_iter)
+                eps = eps.detach().float().contiguous()
+                mu_t, lv_t = self._raw(run, node.mu), self._raw(run, node.lv)
+                c = node.mu.c
+                z = torch.empty(n, node.mu.h, node.mu.w, c, dtype=dtype, device=dev)
+                mu_o = torch.empty(n, c, node.mu.h, node.mu.w, dtype=torch.float32, device=dev)
+                lv_o = torch.empty_like(mu_o)
+                ops.reparam_fwd(mu_t, 0, lv_t, 0, eps, c, z, mu_o, lv_o, None)
+                run.ext[node.z.id] = z
+                run.reparam[node] = (eps, mu_o, lv_o)
+            else:   # HeadNode
+                x = self._materialize(run, node.inp, L.MODE_PLAIN, 0, dtype)
+                wk = head_weight(node.holder)
+                score = torch.empty(n, dtype=torch.float32, device=dev)
+                wn2 = torch.empty(1, dtype=torch.float32, device=dev)
+                ops.dhead_fwd(x, wk, node.holder.bias.detach(), score, wn2)
+                run.head[node] = (x, wk, wn2, score)
+        for obj, kind in self.outputs:
+            if kind == "score":
+                outs.append(run.head[obj][3])
+            elif kind == "mu":
+                outs.append(run.reparam[obj][1])
+            elif kind == "logvar":
+                outs.append(run.reparam[obj][2])
+            else:
+                outs.append(self._export(run, obj, dtype))
+        if not keep:
+            run = None
+        return outs, run
+
+    def _export(self, run, act, dtype):
+        """finished activation -> NCHW fp32 (API boundary)."""
+        if act.kind == "conv" and not act.norm and act.act == L.ACT_NONE and act.res is None:
+            src = run.Y[act.producer]
+        elif act.kind != "conv":
+            src = run.ext[act.id]
+        else:
+            src = self._materialize(run, act, L.MODE_PLAIN, 0, dtype)
+        out = torch.empty(self.n, act.c_log, act.h, act.w, dtype=torch.float32, device=src.device)
+        return ops.unpack_nchw(src, act.c_log, out)
+
+    # ------------------------------------------------------------------ backward
+    def run_backward(self, run, grads, need_input_grad=(False,)):
+        """grads: one NCHW fp32 tensor (or None) per plan output, in output order.
+        Accumulates parameter gradients into .grad; returns input gradients (NCHW fp32 or None)."""
+        dtype = _STATE["dtype"]
+        n = self.n
+        dense = {}        # act id -> list of dense NHWC grad tensors
+        dxp = {}          # conv node -> padded-input gradient
+        ext_mu, ext_lv, gscores = {}, {}, {}
+        dev = None
+        for (obj, kind), g in zip(self.outputs, grads):
+            if g is None:
+                continue
+            dev = g.device
+            g = g.detach()
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                g = g.float().contiguous()
+            if kind == "score":
+                gscores[obj] = g
+            elif kind == "mu":
+                ext_mu[obj] = g
+            elif kind == "logvar":
+                ext_lv[obj] = g
+            else:
+                t = torch.empty(n, obj.h, obj.w, obj.c, dtype=dtype, device=dev)
+                ops.pack_nchw(g, t)
+                dense.setdefault(obj.id, []).append(t)
+        if dev is None:
+            return [None] * len(self.inputs)
+
+        def sources(act, seen=None):
+            s = [(t, L.MODE_PLAIN, 0) for t in dense.get(act.id, ())]
+            for c in act.consumers:
+                if isinstance(c, ConvNode) and c in dxp:
+                    s.append((dxp[c], c.mode, c.pad))
+            for p in act.passthrough:
+                s.extend(sources(p))
+            return s
+
+        def needs_dx(act):
+            if act.kind == "ext":
+                return need_input_grad[self.inputs.index(act)]
+            return True
+
+        for node in reversed(self.nodes):
+            if isinstance(node, HeadNode):
+                gs = gscores.get(node)
+                if gs is None:
+                    continue
+                x, wk, wn2, _ = run.head[node]
+                k = wk.numel()
+                dx = torch.empty_like(x)
+                scratch = torch.empty(k + 8, dtype=torch.float32, device=dev)
+                h = node.holder
+                want_w = _wants_grad(h.weight_orig)
+                dwk = ops.zero_(torch.empty(k, dtype=torch.float32, device=dev)) if want_w else None
+                db = ops.zero_(torch.empty(4, dtype=torch.float32, device=dev)) if want_w else None
+                ops.dhead_bwd(x, wk, wn2, gs, dx, dwk, db, scratch)
+                if want_w:
+                    co, ci, kh, kw = h.weight_orig.shape
+                    gw = dwk.view(kh, kw, ci).permute(2, 0, 1).reshape(co, ci, kh, kw)
+                    if h.weight_orig.grad is None:
+                        h.weight_orig.grad = gw.contiguous()
+                    else:
+                        h.weight_orig.grad.add_(gw)
+                    if h.bias.grad is None:
+                        h.bias.grad = db[:1].clone()
+                    else:
+                        h.bias.grad.add_(db[:1])
+                dense.setdefault(node.inp.id, []).append(dx)
+            elif isinstance(node, ReparamNode):
+                srcs = sources(node.z)
+                gm, gl = ext_mu.get(node), ext_lv.get(node)
+                if not srcs and gm is None and gl is None:
+                    continue
+                c, h, w = node.mu.c, node.mu.h, node.mu.w
+                dz = torch.empty(n, h, w, c, dtype=dtype, device=dev)
+                if srcs:
+                    ops.xform_bwd_gather(srcs, None, n, h, w, c, dz, 0)
+                else:
+                    ops.zero_(dz)
+                dmu, dlv = torch.empty_like(dz), torch.empty_like(dz)
+                eps = run.reparam[node][0]
+                ops.reparam_bwd(self._raw(run, node.mu), 0, self._raw(run, node.lv), 0, eps, dz, c, dmu, dlv, gm, gl, 0.0)
+                dense.setdefault(node.mu.id, []).append(dmu)
+                dense.setdefault(node.lv.id, []).append(dlv)
+            else:
+                srcs = []
+                for a in node.out_acts:
+                    srcs.extend(sources(a))
+                if not srcs:
+                    continue          # dead branch: nothing downstream needs this layer's gradient
+                a0, spec, holder = node.out_acts[0], node.spec, node.holder
+                halo = spec.pkh - 1
+                dy = ops.zero_(torch.empty(n, a0.h + 2 * halo, a0.w + 2 * halo, spec.out_c, dtype=dtype, device=dev))
+                y = run.Y[node]
+                if y.dtype != dtype:          # fp32-stored final image in bf16 mode: no norm/act there
+                    y = None
+                pc = packed_for(holder, spec)
+                want_w = _wants_grad(holder.weight)
+                dw, dbias = pc.grad_buffers() if want_w else (None, None)
+                if want_w:
+                    ops.zero_(dbias)
+                if a0.norm:
+                    mr = run.MR[node]
+                    gs = ops.zero_(torch.empty(n * spec.co * 2, dtype=torch.float32, device=dev))
+                    ops.xform_bwd_gather(srcs, y, n, a0.h, a0.w, spec.out_c, dy, halo, mr, a0.act, node.pre_act, gs, None)
+                    ops.xform_bwd_norm(y, n, a0.h, a0.w, spec.out_c, dy, halo, mr, gs, node.pre_act, dbias)
+                else:
+                    ops.xform_bwd_gather(srcs, y, n, a0.h, a0.w, spec.out_c, dy, halo, None, a0.act, node.pre_act, None, dbias)
+                xp = run.xp_of_node[node]
+                if want_w:
+                    ops.zero_(dw)
+                    ops.conv_wgrad(spec, xp, dy, dw)
+                    _accumulate_grad(holder.weight, lambda g, acc: ops.wunpack_grad(spec, dw, g, acc))
+                    if _wants_grad(holder.bias):
+                        db = dbias[:spec.co]
+                        if holder.bias.grad is None:
+                            holder.bias.grad = db.clone()
+                        else:
+                            holder.bias.grad.add_(db)
+                if needs_dx(node.inp):
+                    pc.refresh(dtype)
+                    g = torch.empty_like(xp)
+                    ops.conv_dgrad(spec, dy, pc.wkT, g)
+                    dxp[node] = g
+        res = []
+        for a, need in zip(self.inputs, need_input_grad):
+            srcs = sources(a) if need else []
+            if not srcs:
+                res.append(None)
+                continue
+            g = torch.empty(n, a.h, a.w, a.c, dtype=dtype, device=dev)
+            ops.xform_bwd_gather(srcs, None, n, a.h, a.w, a.c, g, 0)
+            out = torch.empty(n, a.c_log, a.h, a.w, dtype=torch.float32, device=dev)
+            res.append(ops.unpack_nchw(g, a.c_log, out))
+        return res
+
+
+def head_weight(holder):
+    """(1,512,16,16) weight_orig -> fp32 vector in (h,w,c) order, cached by version."""
+    w = holder.weight_orig
+    key = (w._version, getattr(w, "_vcg_epoch", 0), w.data_ptr(), w.device)
+    cache = holder.__dict__.setdefault("_vcg_head", {})
+    if cache.get("key") != key:
+        cache["w"] = w.detach()[0].permute(1, 2, 0).contiguous().view(-1)
+        cache["key"] = key
+    return cache["w"]
