@@ -162,13 +162,15 @@ VCG_API int vcg_unpack_nchw(int32_t dtype, const void* src, int32_t src_c, int32
 
 /* ------------------------------------------------------------------------------------------ */
 /* VAE reparameterisation + KL (Networks.py:219-227, Losses.py:115-121).                       */
-/* z = mu + eps*exp(0.5*clamp(lv,-10,10)); logvar_out = clamp(lv); kl_sum += sum(1+lv-mu^2-e^lv) */
-VCG_API int vcg_reparam_fwd(int32_t dtype, const void* mu, int32_t mu_pitch, const void* lv, int32_t lv_pitch,
+/* z = mu + eps*exp(0.5*clamp(lv,-10,10)); logvar_out = clamp(lv); kl_sum += sum(1+lv-mu^2-e^lv).
+ * mu / lv are the fp32 NHWC outputs of the mu and logvar convolutions (kept in fp32 in both modes: logvar
+ * reaches +-10 and feeds exp()); dtype is the element type of z / dz / dmu / dlv.                          */
+VCG_API int vcg_reparam_fwd(int32_t dtype, const float* mu, int32_t mu_pitch, const float* lv, int32_t lv_pitch,
                     const float* eps /*NCHW fp32*/, int32_t n, int32_t hw, int32_t c,
                     void* z /*dense NHWC c*/, float* mu_out /*NCHW*/, float* lv_out /*NCHW*/,
                     float* kl_sum, void* stream);
 /* dmu = dz + gmu_ext + kl_scale*mu ; dlv = mask*(dz*eps*0.5*std + glv_ext - 0.5*kl_scale*(1-e^lv)) */
-VCG_API int vcg_reparam_bwd(int32_t dtype, const void* mu, int32_t mu_pitch, const void* lv, int32_t lv_pitch,
+VCG_API int vcg_reparam_bwd(int32_t dtype, const float* mu, int32_t mu_pitch, const float* lv, int32_t lv_pitch,
                     const float* eps, const void* dz, int32_t dz_pitch,
                     const float* gmu_ext /*NCHW or NULL*/, const float* glv_ext /*NCHW or NULL*/,
                     float kl_scale, int32_t n, int32_t hw, int32_t c,

@@ -235,12 +235,12 @@ def test_reparam(K, prec):
     mu_g1, lv_g1 = mu.grad.clone(), lv.grad.clone()
     mu.grad = lv.grad = None
     ((z * G).sum() + (mu * gmu_e).sum() + (lvc * glv_e).sum()).backward()
-    # ours: mu in a fused buffer with channel offset 0 / pitch 2c, lv dense
-    both = torch.zeros(n, h, w, 2 * c, dtype=dt, device="cuda")
-    tmp = torch.empty(n, h, w, c, dtype=dt, device="cuda")
+    # ours: mu / logvar are fp32 NHWC conv outputs in both modes; mu sits in a wider buffer (pitch 2c)
+    both = torch.zeros(n, h, w, 2 * c, dtype=torch.float32, device="cuda")
+    tmp = torch.empty(n, h, w, c, dtype=torch.float32, device="cuda")
     ops.pack_nchw(mu.detach(), tmp)
     both[..., :c] = tmp
-    lvb = torch.empty(n, h, w, c, dtype=dt, device="cuda")
+    lvb = torch.empty(n, h, w, c, dtype=torch.float32, device="cuda")
     ops.pack_nchw(lv.detach(), lvb)
     zb = torch.empty(n, h, w, c, dtype=dt, device="cuda")
     mu_o, lv_o = torch.empty(n, c, h, w, device="cuda"), torch.empty(n, c, h, w, device="cuda")

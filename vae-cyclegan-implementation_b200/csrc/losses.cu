@@ -82,7 +82,7 @@ kl_kernel(const float* __restrict__ mu, const float* __restrict__ lv, long long 
 // ------------------------------------------------------------------ reparameterisation
 template <typename T>
 __global__ void __launch_bounds__(256)
-reparam_fwd_kernel(const T* __restrict__ mu, int mu_pitch, const T* __restrict__ lv, int lv_pitch,
+reparam_fwd_kernel(const float* __restrict__ mu, int mu_pitch, const float* __restrict__ lv, int lv_pitch,
                    const float* __restrict__ eps, int n, int hw, int c, T* __restrict__ z, float* __restrict__ mu_out,
                    float* __restrict__ lv_out, float* __restrict__ kl_sum) {
   const long long total = static_cast<long long>(n) * hw * c;
@@ -92,8 +92,8 @@ reparam_fwd_kernel(const T* __restrict__ mu, int mu_pitch, const T* __restrict__
     const int ch = static_cast<int>(i % c);
     const long long pix = i / c;                       // n*hw + p
     const int ni = static_cast<int>(pix / hw), pp = static_cast<int>(pix - static_cast<long long>(ni) * hw);
-    const float m = Elem<T>::ld(mu + pix * mu_pitch + ch);
-    const float l = Elem<T>::ld(lv + pix * lv_pitch + ch);
+    const float m = mu[pix * mu_pitch + ch];
+    const float l = lv[pix * lv_pitch + ch];
     const float lc = fminf(fmaxf(l, -10.f), 10.f);
     const long long nchw = (static_cast<long long>(ni) * c + ch) * hw + pp;
     const float e = eps[nchw];
@@ -109,7 +109,7 @@ reparam_fwd_kernel(const T* __restrict__ mu, int mu_pitch, const T* __restrict__
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-reparam_bwd_kernel(const T* __restrict__ mu, int mu_pitch, const T* __restrict__ lv, int lv_pitch,
+reparam_bwd_kernel(const float* __restrict__ mu, int mu_pitch, const float* __restrict__ lv, int lv_pitch,
                    const float* __restrict__ eps, const T* __restrict__ dz, int dz_pitch,
                    const float* __restrict__ gmu_ext, const float* __restrict__ glv_ext, float kl_scale, int n, int hw,
                    int c, T* __restrict__ dmu, int dmu_pitch, T* __restrict__ dlv, int dlv_pitch) {
@@ -119,8 +119,8 @@ reparam_bwd_kernel(const T* __restrict__ mu, int mu_pitch, const T* __restrict__
     const int ch = static_cast<int>(i % c);
     const long long pix = i / c;
     const int ni = static_cast<int>(pix / hw), pp = static_cast<int>(pix - static_cast<long long>(ni) * hw);
-    const float m = Elem<T>::ld(mu + pix * mu_pitch + ch);
-    const float l = Elem<T>::ld(lv + pix * lv_pitch + ch);
+    const float m = mu[pix * mu_pitch + ch];
+    const float l = lv[pix * lv_pitch + ch];
     const float lc = fminf(fmaxf(l, -10.f), 10.f);
     const long long nchw = (static_cast<long long>(ni) * c + ch) * hw + pp;
     const float g = Elem<T>::ld(dz + pix * dz_pitch + ch);
@@ -239,38 +239,35 @@ extern "C" int vcg_kl_fwd_bwd(const float* mu, const float* lv, int64_t numel, f
   return VCG_OK;
 }
 
-extern "C" int vcg_reparam_fwd(int32_t dtype, const void* mu, int32_t mu_pitch, const void* lv, int32_t lv_pitch,
+extern "C" int vcg_reparam_fwd(int32_t dtype, const float* mu, int32_t mu_pitch, const float* lv, int32_t lv_pitch,
                                const float* eps, int32_t n, int32_t hw, int32_t c, void* z, float* mu_out, float* lv_out,
                                float* kl_sum, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VCG_REQUIRE((mu_out == nullptr) == (lv_out == nullptr), VCG_E_INVALID, "reparam_fwd: mu_out/lv_out together");
   const int grid = grid_for(static_cast<long long>(n) * hw * c, 1);
   if (dtype == VCG_F32)
-    reparam_fwd_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(mu), mu_pitch, static_cast<const float*>(lv),
-                                                        lv_pitch, eps, n, hw, c, static_cast<float*>(z), mu_out, lv_out, kl_sum);
+    reparam_fwd_kernel<float><<<grid, 256, 0, stream>>>(mu, mu_pitch, lv, lv_pitch, eps, n, hw, c, static_cast<float*>(z),
+                                                        mu_out, lv_out, kl_sum);
   else
-    reparam_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(mu), mu_pitch,
-                                                                static_cast<const __nv_bfloat16*>(lv), lv_pitch, eps, n, hw, c,
+    reparam_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(mu, mu_pitch, lv, lv_pitch, eps, n, hw, c,
                                                                 static_cast<__nv_bfloat16*>(z), mu_out, lv_out, kl_sum);
   VCG_CHECK_LAUNCH("reparam_fwd_kernel");
   return VCG_OK;
 }
 
-extern "C" int vcg_reparam_bwd(int32_t dtype, const void* mu, int32_t mu_pitch, const void* lv, int32_t lv_pitch,
+extern "C" int vcg_reparam_bwd(int32_t dtype, const float* mu, int32_t mu_pitch, const float* lv, int32_t lv_pitch,
                                const float* eps, const void* dz, int32_t dz_pitch, const float* gmu_ext,
                                const float* glv_ext, float kl_scale, int32_t n, int32_t hw, int32_t c, void* dmu,
                                int32_t dmu_pitch, void* dlv, int32_t dlv_pitch, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int grid = grid_for(static_cast<long long>(n) * hw * c, 1);
   if (dtype == VCG_F32)
-    reparam_bwd_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(mu), mu_pitch, static_cast<const float*>(lv),
-                                                        lv_pitch, eps, static_cast<const float*>(dz), dz_pitch, gmu_ext, glv_ext,
-                                                        kl_scale, n, hw, c, static_cast<float*>(dmu), dmu_pitch,
-                                                        static_cast<float*>(dlv), dlv_pitch);
+    reparam_bwd_kernel<float><<<grid, 256, 0, stream>>>(mu, mu_pitch, lv, lv_pitch, eps, static_cast<const float*>(dz), dz_pitch,
+                                                        gmu_ext, glv_ext, kl_scale, n, hw, c, static_cast<float*>(dmu),
+                                                        dmu_pitch, static_cast<float*>(dlv), dlv_pitch);
   else
     reparam_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(mu), mu_pitch, static_cast<const __nv_bfloat16*>(lv), lv_pitch, eps,
-        static_cast<const __nv_bfloat16*>(dz), dz_pitch, gmu_ext, glv_ext, kl_scale, n, hw, c,
+        mu, mu_pitch, lv, lv_pitch, eps, static_cast<const __nv_bfloat16*>(dz), dz_pitch, gmu_ext, glv_ext, kl_scale, n, hw, c,
         static_cast<__nv_bfloat16*>(dmu), dmu_pitch, static_cast<__nv_bfloat16*>(dlv), dlv_pitch);
   VCG_CHECK_LAUNCH("reparam_bwd_kernel");
   return VCG_OK;

@@ -285,14 +285,16 @@ def _off(t, c_off):
 
 def reparam_fwd(mu_src, mu_off, lv_src, lv_off, eps, c, z, mu_out, lv_out, kl_sum=None):
     n, h, w, _ = mu_src.shape
-    L.check(L.load().vcg_reparam_fwd(L.dtype_code(mu_src.dtype), _off(mu_src, mu_off), mu_src.shape[-1],
+    assert mu_src.dtype == torch.float32 and lv_src.dtype == torch.float32
+    L.check(L.load().vcg_reparam_fwd(L.dtype_code(z.dtype), _off(mu_src, mu_off), mu_src.shape[-1],
                                      _off(lv_src, lv_off), lv_src.shape[-1], L.ptr(eps), n, h * w, c, L.ptr(z),
                                      L.ptr(mu_out), L.ptr(lv_out), L.ptr(kl_sum), L.stream_ptr()), "vcg_reparam_fwd")
 
 
 def reparam_bwd(mu_src, mu_off, lv_src, lv_off, eps, dz, c, dmu, dlv, gmu_ext=None, glv_ext=None, kl_scale=0.0):
     n, h, w, _ = mu_src.shape
-    L.check(L.load().vcg_reparam_bwd(L.dtype_code(mu_src.dtype), _off(mu_src, mu_off), mu_src.shape[-1],
+    assert mu_src.dtype == torch.float32 and lv_src.dtype == torch.float32
+    L.check(L.load().vcg_reparam_bwd(L.dtype_code(dz.dtype), _off(mu_src, mu_off), mu_src.shape[-1],
                                      _off(lv_src, lv_off), lv_src.shape[-1], L.ptr(eps), L.ptr(dz), dz.shape[-1],
                                      L.ptr(gmu_ext), L.ptr(glv_ext), kl_scale, n, h * w, c, L.ptr(dmu), dmu.shape[-1],
                                      L.ptr(dlv), dlv.shape[-1], L.stream_ptr()), "vcg_reparam_bwd")

@@ -246,6 +246,7 @@ class Plan:
             run.ext[a.id] = t
         eps_iter = iter(eps_list)
         outs = []
+        node_out = {}
         out_nodes = {id(o[0]): o[1] for o in self.outputs}
         for node in self.nodes:
             if isinstance(node, ConvNode):
@@ -254,10 +255,14 @@ class Plan:
                 pc = packed_for(node.holder, node.spec).refresh(dtype)
                 a0 = node.out_acts[0]
                 # the final image layer (conv -> Identity, no norm, Networks.py:192) is stored in fp32
-                final_image = (dtype != torch.float32 and len(node.out_acts) == 1 and id(a0) in out_nodes
-                               and not a0.consumers and not a0.norm and a0.act == L.ACT_NONE
-                               and node.pre_act == L.ACT_NONE)
-                y = torch.empty(n, a0.h, a0.w, node.spec.out_c, dtype=torch.float32 if final_image else dtype, device=dev)
+                # and so are the bottleneck's mu / logvar convs (Networks.py:217-218): logvar reaches +-10 and
+                # feeds exp(), where a bf16 ulp (0.0625 at |x|>=8) would cost 3% on sigma
+                plain = (dtype != torch.float32 and len(node.out_acts) == 1 and not a0.norm
+                         and a0.act == L.ACT_NONE and node.pre_act == L.ACT_NONE)
+                final_image = plain and id(a0) in out_nodes and not a0.consumers
+                bottleneck = plain and bool(a0.consumers) and all(isinstance(c, ReparamNode) for c in a0.consumers)
+                y = torch.empty(n, a0.h, a0.w, node.spec.out_c,
+                                dtype=torch.float32 if (final_image or bottleneck) else dtype, device=dev)
                 bias = node.holder.bias.detach()
                 if a0.norm and dtype == torch.bfloat16:
                     acc = ops.zero_(torch.empty(n * node.spec.co * 2, dtype=torch.float32, device=dev))
@@ -279,21 +284,25 @@ class Plan:
                 lv_o = torch.empty_like(mu_o)
                 ops.reparam_fwd(mu_t, 0, lv_t, 0, eps, c, z, mu_o, lv_o, None)
                 run.ext[node.z.id] = z
-                run.reparam[node] = (eps, mu_o, lv_o)
+                run.reparam[node] = (eps,)
+                node_out[node] = (mu_o, lv_o)
             else:   # HeadNode
                 x = self._materialize(run, node.inp, L.MODE_PLAIN, 0, dtype)
                 wk = head_weight(node.holder)
                 score = torch.empty(n, dtype=torch.float32, device=dev)
                 wn2 = torch.empty(1, dtype=torch.float32, device=dev)
                 ops.dhead_fwd(x, wk, node.holder.bias.detach(), score, wn2)
-                run.head[node] = (x, wk, wn2, score)
+                # NOTE: tensors returned to autograd must not be stored in `run` (ctx -> run -> output ->
+                # grad_fn -> ctx would be a reference cycle that only the cyclic GC frees: GBs per step)
+                run.head[node] = (x, wk, wn2)
+                node_out[node] = (score,)
         for obj, kind in self.outputs:
             if kind == "score":
-                outs.append(run.head[obj][3])
+                outs.append(node_out[obj][0])
             elif kind == "mu":
-                outs.append(run.reparam[obj][1])
+                outs.append(node_out[obj][0])
             elif kind == "logvar":
-                outs.append(run.reparam[obj][2])
+                outs.append(node_out[obj][1])
             else:
                 outs.append(self._export(run, obj, dtype))
         if not keep:
@@ -360,7 +369,7 @@ class Plan:
                 gs = gscores.get(node)
                 if gs is None:
                     continue
-                x, wk, wn2, _ = run.head[node]
+                x, wk, wn2 = run.head[node]
                 k = wk.numel()
                 dx = torch.empty_like(x)
                 scratch = torch.empty(k + 8, dtype=torch.float32, device=dev)
