@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=2, help="bounded CPU sample: batch of the reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (vcg_b200.graph.GraphedStep)")
     return ap.parse_args()
 
 
@@ -188,11 +189,20 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    if args.graph:
+        from vcg_b200.graph import GraphedStep
+        runner = GraphedStep(model, {"x": x_dev, "y": y_dev}, warmup=2)
+    else:
+        runner = model.training_step
+
     def step_resident():
-        return model.training_step({"x": x_dev, "y": y_dev})
+        return runner({"x": x_dev, "y": y_dev})
 
     def step_e2e():
-        return model.training_step({"x": x_host.to(dev, non_blocking=True), "y": y_host.to(dev, non_blocking=True)})
+        # graph mode: GraphedStep copies the pinned host batch straight into its static device buffers
+        if args.graph:
+            return runner({"x": x_host, "y": y_host})
+        return runner({"x": x_host.to(dev, non_blocking=True), "y": y_host.to(dev, non_blocking=True)})
 
     for _ in range(args.warmup):
         last = step_resident()
@@ -201,10 +211,20 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     n0 = lib.launch_count()
-    ops.prof_begin()
+    if not args.graph:
+        ops.prof_begin()
     ms = timed(step_resident, args.steps)
-    records = ops.prof_end()
+    records = ops.prof_end() if not args.graph else []
     launches = lib.launch_count() - n0
+    if args.graph:
+        # kernels inside a replayed graph are not re-issued by the library, so they are neither counted nor
+        # event-timed there: run the same steps once more eagerly (after the timed region) to count the
+        # launches one step consists of and to time the conv GEMM launches with CUDA events
+        n0 = lib.launch_count()
+        ops.prof_begin()
+        ms_eager = timed(lambda: model.training_step({"x": x_dev, "y": y_dev}), args.steps)
+        records = ops.prof_end()
+        launches = lib.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     value = args.global_batch * args.steps / (ms / 1e3)
     # ---- end-to-end through the public API with host buffers
@@ -217,11 +237,22 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel family
     fam = {}
-    for kind, flops, s, e in records:
+    layers = {}
+    for kind, flops, tag, s, e in records:
         f = fam.setdefault(kind, [0.0, 0.0, 0])
+        dt = s.elapsed_time(e)
         f[0] += flops
-        f[1] += s.elapsed_time(e)
+        f[1] += dt
         f[2] += 1
+        l = layers.setdefault((kind, tag), [0.0, 0.0, 0])
+        l[0] += flops
+        l[1] += dt
+        l[2] += 1
+    if rank == 0 and os.environ.get("VCG_BENCH_LAYERS"):
+        with open(os.environ["VCG_BENCH_LAYERS"], "w") as fh:
+            for (kind, tag), v in sorted(layers.items(), key=lambda kv: -kv[1][1]):
+                fh.write(f"{kind:11s} {tag:22s} launches/step {v[2] / args.steps:5.1f}  ms/step {v[1] / args.steps:8.3f}  "
+                         f"TFLOP/s {v[0] / max(v[1], 1e-9) / 1e9:8.1f}\n")
     pk = peaks()
     tc_flops = sum(fam.get(k, [0, 0, 0])[0] for k in ("conv_fwd", "conv_dgrad"))
     tc_ms = sum(fam.get(k, [0, 0, 0])[1] for k in ("conv_fwd", "conv_dgrad"))
@@ -248,7 +279,9 @@ def run_ours(args):
                                "256x256 training step, global batch %d, per-GPU batch %d" % (args.global_batch, per),
                    "global_batch": args.global_batch, "parallelism": f"dp{world}", "latent_dim": 64,
                    "l2": "working set (weights 276 MB bf16 + >10 GB activations per step) exceeds the 126 MB L2; no flush needed",
-                   "dead_passes_skipped": True},
+                   "dead_passes_skipped": True, "cuda_graph": bool(args.graph),
+                   "roofline_timing": ("conv GEMM launches event-timed in an eager re-run of the same steps right after the "
+                                       "graph-replayed timed region" if args.graph else "event-timed inside the timed region")},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},

@@ -201,9 +201,10 @@ VCG_API int vcg_dhead_bwd(int32_t dtype, const void* x, const float* w_khwc, con
 typedef struct vcg_adam_chunk {  /* one <=65536-element slice of one tensor */
   float* p; const float* g; float* m; float* v; int32_t numel;
 } vcg_adam_chunk;
-VCG_API int vcg_adam_multi(const vcg_adam_chunk* chunks_dev, int32_t nchunks, float lr, float beta1,
-                   float beta2, float eps, float bias_corr1, float bias_corr2_sqrt,
-                   float grad_scale, void* stream);
+/* state_dev: 4 device floats {step, lr/bias_corr1, sqrt(bias_corr2), -}: the step counter is advanced
+ * and the bias corrections are recomputed ON THE DEVICE by each call (CUDA-graph replayable).          */
+VCG_API int vcg_adam_multi(const vcg_adam_chunk* chunks_dev, int32_t nchunks, float* state_dev, float lr,
+                           float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* test hook: encode a bf16 SWIZZLE_128B tiled TMA descriptor only (no launch) */
 VCG_API int vcg_probe_tmap(const void* base, int32_t rank, const uint64_t* dims,

@@ -311,12 +311,14 @@ def test_adam_multi(K):
     for i, ck in enumerate(chunks):
         arr[i].p, arr[i].g, arr[i].m, arr[i].v, arr[i].numel = ck
     table = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).cuda()
+    state = torch.zeros(4, device="cuda")
     for step in range(1, 4):
         for i, (r, g) in enumerate(zip(ref, gs)):
             g.copy_(rnd(*r.shape, seed=100 * step + i))
             r.grad = g.clone()
         opt.step()
-        ops.adam_multi(table, len(chunks), 2e-4, 0.5, 0.999, 1e-8, step)
+        ops.adam_multi(table, len(chunks), state, 2e-4, 0.5, 0.999, 1e-8)
+        assert float(state[0]) == step
         for r, p in zip(ref, ps):
             assert rel_l2(p, r.detach()) < 1e-7, (step, rel_l2(p, r.detach()))
 

@@ -318,6 +318,10 @@ class _Composite(_PlanModule):
             import torch.distributed as dist
             dist.all_reduce(vals, op=dist.ReduceOp.SUM, group=sync.group)
             vals = vals / sync.world
+        sink = getattr(self, "_vcg_capture", None)
+        if sink is not None:            # CUDA-graph capture (graph.py): no host read inside the captured region
+            sink["keys"], sink["vals"] = keys, vals
+            return {}
         return dict(zip(keys, vals.tolist()))
 
     @staticmethod

@@ -73,6 +73,8 @@ int vcg_conv_fwd_tc(const vcg_conv_desc*, const void*, const void*, const float*
 int vcg_conv_wgrad_tc(const vcg_conv_desc*, const void*, const void*, int, int, float*, cudaStream_t);
 int vcg_conv_fwd_simt(const vcg_conv_desc*, int, const void*, const void*, const float*, void*, int, cudaStream_t);
 int vcg_conv_wgrad_simt(const vcg_conv_desc*, int, const void*, const void*, int, int, float*, cudaStream_t);
+int vcg_conv_wgrad_thin(const vcg_conv_desc*, const void*, const void*, int, int, float*, cudaStream_t);
+bool vcg_wgrad_thin_supported(const vcg_conv_desc*);
 
 static bool force_simt() {
   static int v = -1;
@@ -101,6 +103,8 @@ extern "C" int vcg_conv_wgrad(const vcg_conv_desc* d, const void* x, const void*
   // into 64-pixel TMA boxes (inputs smaller than 256x256) stay on the SIMT kernel
   const int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
   const bool tileable = wo >= 64 ? (wo % 64 == 0) : (64 % wo == 0 && ho % (64 / wo) == 0);
+  // bf16 mode, cout <= 4 (the 64->3 output convolution): register-blocked FFMA kernel (M=3 is no tcgen05 shape)
+  if (d->dtype == VCG_BF16 && !force_simt() && vcg_wgrad_thin_supported(d)) return vcg_conv_wgrad_thin(d, x, dy, dy_halo, dy_c, dw, stream);
   if (d->dtype == VCG_F32 || force_simt() || d->cout < 16 || !tileable)
     return vcg_conv_wgrad_simt(d, d->dtype, x, dy, dy_halo, dy_c, dw, stream);
   return vcg_conv_wgrad_tc(d, x, dy, dy_halo, dy_c, dw, stream);

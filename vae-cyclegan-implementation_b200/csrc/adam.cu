@@ -16,9 +16,19 @@ __device__ __forceinline__ float lerp_like_torch(float a, float b, float w) {
   return w < 0.5f ? a + w * d : b - d * (1.f - w);
 }
 
+// Device-side step counter and bias corrections: state = {step, lr/bc1, sqrt(bc2), unused}.  Keeping them on
+// the device makes the optimiser step CUDA-graph replayable (no host scalar is baked into the launch).
+__global__ void adam_tick_kernel(float* __restrict__ state, float lr, float beta1, float beta2) {
+  const double step = static_cast<double>(state[0]) + 1.0;
+  state[0] = static_cast<float>(step);
+  state[1] = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(beta1), step)));
+  state[2] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
+}
+
 __global__ void __launch_bounds__(256)
-adam_multi_kernel(const vcg_adam_chunk* __restrict__ chunks, float lr_over_bc1, float beta1, float beta2, float eps,
-                  float bc2_sqrt, float grad_scale) {
+adam_multi_kernel(const vcg_adam_chunk* __restrict__ chunks, const float* __restrict__ state, float beta1, float beta2,
+                  float eps, float grad_scale) {
+  const float lr_over_bc1 = state[1], bc2_sqrt = state[2];
   const vcg_adam_chunk ck = chunks[blockIdx.x];
   const int n = ck.numel;
   const float w1 = 1.f - beta1, w2 = 1.f - beta2;
@@ -54,12 +64,13 @@ adam_multi_kernel(const vcg_adam_chunk* __restrict__ chunks, float lr_over_bc1, 
 
 }  // namespace
 
-extern "C" int vcg_adam_multi(const vcg_adam_chunk* chunks_dev, int32_t nchunks, float lr, float beta1, float beta2,
-                              float eps, float bias_corr1, float bias_corr2_sqrt, float grad_scale, void* stream) {
+extern "C" int vcg_adam_multi(const vcg_adam_chunk* chunks_dev, int32_t nchunks, float* state_dev, float lr, float beta1,
+                              float beta2, float eps, float grad_scale, void* stream) {
   if (nchunks <= 0) return VCG_OK;
-  VCG_REQUIRE(bias_corr1 != 0.f && bias_corr2_sqrt != 0.f, VCG_E_INVALID, "adam: zero bias correction");
-  adam_multi_kernel<<<nchunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(chunks_dev, lr / bias_corr1, beta1, beta2, eps,
-                                                                           bias_corr2_sqrt, grad_scale);
+  VCG_REQUIRE(state_dev, VCG_E_INVALID, "adam: device state is NULL");
+  adam_tick_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(state_dev, lr, beta1, beta2);
+  VCG_CHECK_LAUNCH("adam_tick_kernel");
+  adam_multi_kernel<<<nchunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(chunks_dev, state_dev, beta1, beta2, eps, grad_scale);
   VCG_CHECK_LAUNCH("adam_multi_kernel");
   return VCG_OK;
 }

@@ -81,8 +81,8 @@ _SIGS = {
     "vcg_dhead_fwd": (C.c_int, [i32, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vcg_dhead_bwd": (C.c_int, [i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
-    "vcg_adam_multi": (C.c_int, [C.c_void_p, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
-                                 C.c_float, C.c_void_p]),
+    "vcg_adam_multi": (C.c_int, [C.c_void_p, i32, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                 C.c_void_p]),
     "vcg_probe_tmap": (C.c_int, [C.c_void_p, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "vcg_zero": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
 }

@@ -30,12 +30,12 @@ def prof_end():
     return r
 
 
-def _rec(kind, flops):
+def _rec(kind, flops, tag=""):
     if _Prof.records is None:
         return None
     s = torch.cuda.Event(enable_timing=True)
     s.record()
-    return (kind, flops, s)
+    return (kind, flops, tag, s)
 
 
 def _rec_end(tok):
@@ -138,7 +138,7 @@ def conv_fwd(spec: ConvSpec, x_pad, w_packed, bias, y, stats_acc=None, act=L.ACT
                    stats=1 if stats_acc is not None else 0, flat=0,
                    out_f32=1 if (y.dtype == torch.float32 and x_pad.dtype != torch.float32) else 0)
     assert tuple(y.shape[:3]) == (n, hp - spec.pkh + 1, wp - spec.pkw + 1), (y.shape, x_pad.shape)
-    tok = _rec("conv_fwd", spec.flops(n, y.shape[1], y.shape[2]))
+    tok = _rec("conv_fwd", spec.flops(n, y.shape[1], y.shape[2]), f"{spec.ci}->{spec.co} k{spec.kh} @{y.shape[1]}")
     L.check(L.load().vcg_conv_fwd(C.byref(d), L.ptr(x_pad), L.ptr(w_packed), L.ptr(bias), L.ptr(y), L.ptr(stats_acc),
                                   L.stream_ptr()), "vcg_conv_fwd")
     _rec_end(tok)
@@ -153,7 +153,8 @@ def conv_dgrad(spec: ConvSpec, dy_pad, w_dgrad, dxp):
                    kwc_pad=spec.d_kwc_pad, cout=spec.cin_phys, cout_pad=spec.d_rows_pad, out_c=dxp.shape[-1],
                    act=L.ACT_NONE, stats=0, flat=1, out_f32=0)
     assert tuple(dxp.shape[:3]) == (n, hd - spec.pkh + 1, wd - spec.pkw + 1), (dxp.shape, dy_pad.shape)
-    tok = _rec("conv_dgrad", spec.flops(n, hd - 2 * (spec.pkh - 1), wd - 2 * (spec.pkw - 1)))
+    tok = _rec("conv_dgrad", spec.flops(n, hd - 2 * (spec.pkh - 1), wd - 2 * (spec.pkw - 1)),
+               f"{spec.ci}->{spec.co} k{spec.kh} @{hd - 2 * (spec.pkh - 1)}")
     L.check(L.load().vcg_conv_fwd(C.byref(d), L.ptr(dy_pad), L.ptr(w_dgrad), None, L.ptr(dxp), None, L.stream_ptr()),
             "vcg_conv_fwd(dgrad)")
     _rec_end(tok)
@@ -169,7 +170,7 @@ def conv_wgrad(spec: ConvSpec, x_pad, dy_pad, dw_packed):
                    kwc_pad=spec.kwc_pad, cout=spec.co, cout_pad=spec.cout_pad, out_c=dy_pad.shape[-1], act=0, stats=0,
                    flat=0, out_f32=0)
     assert dy_pad.shape[1] == hp - spec.pkh + 1 + 2 * halo_h
-    tok = _rec("conv_wgrad", spec.flops(n, hp - spec.pkh + 1, wp - spec.pkw + 1))
+    tok = _rec("conv_wgrad", spec.flops(n, hp - spec.pkh + 1, wp - spec.pkw + 1), f"{spec.ci}->{spec.co} k{spec.kh} @{hp - spec.pkh + 1}")
     L.check(L.load().vcg_conv_wgrad(C.byref(d), L.ptr(x_pad), L.ptr(dy_pad), halo_h, dy_pad.shape[-1], L.ptr(dw_packed),
                                     L.stream_ptr()), "vcg_conv_wgrad")
     _rec_end(tok)
@@ -314,10 +315,9 @@ def dhead_bwd(x, w_khwc, wnorm2, gscore, dx, dw, dbias, scratch):
                                    L.ptr(dx), L.ptr(dw), L.ptr(dbias), L.ptr(scratch), L.stream_ptr()), "vcg_dhead_bwd")
 
 
-def adam_multi(chunks_dev, nchunks, lr, beta1, beta2, eps, step, grad_scale=1.0):
-    bc1 = 1.0 - beta1 ** step
-    bc2_sqrt = (1.0 - beta2 ** step) ** 0.5
-    L.check(L.load().vcg_adam_multi(L.ptr(chunks_dev), nchunks, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale,
+def adam_multi(chunks_dev, nchunks, state_dev, lr, beta1, beta2, eps, grad_scale=1.0):
+    """state_dev: float32[4] device tensor {step, lr/bc1, sqrt(bc2), -}; the call advances step by one."""
+    L.check(L.load().vcg_adam_multi(L.ptr(chunks_dev), nchunks, L.ptr(state_dev), lr, beta1, beta2, eps, grad_scale,
                                     L.stream_ptr()), "vcg_adam_multi")
 
 

@@ -25,6 +25,9 @@ class FusedAdam(torch.optim.Adam):
         self._flat = None
         self._table = None
         self._table_key = None
+        self._dev_state = None      # float32[4] on the device: {step, lr/bc1, sqrt(bc2), -}
+        self._dev_step = 0
+        self._last = None
         self.grad_scale = 1.0       # data-parallel averaging folded into the update (dist.py sets 1/world)
         self.pre_step_hook = None   # dist.py: all-reduce of the flat gradient buffer
 
@@ -98,13 +101,39 @@ class FusedAdam(torch.optim.Adam):
             if key != self._table_key or len(self.param_groups) > 1:
                 self._table = self._build_table(items)
                 self._table_key = key
-            for s in steps:
-                s += 1
-            stepno = int(steps[0].item())
-            if any(int(s.item()) != stepno for s in steps[1:]):
+            before = int(steps[0].item())
+            if any(int(s.item()) != before for s in steps[1:]):
                 raise RuntimeError("FusedAdam: parameters of one group must share the step count")
+            dev = items[0][0].device
+            if self._dev_state is None or self._dev_state.device != dev:
+                self._dev_state = torch.zeros(4, dtype=torch.float32, device=dev)
+                self._dev_step = 0
+            if self._dev_step != before:          # first use / after load_state_dict: resync the device counter
+                self._dev_state[0:1].fill_(float(before))
             table, nchunks = self._table
-            ops.adam_multi(table, nchunks, group["lr"], beta1, beta2, group["eps"], stepno, self.grad_scale)
-            for p, _, _, _ in items:        # the kernel wrote p behind autograd's back: invalidate packed copies
-                p._vcg_epoch = getattr(p, "_vcg_epoch", 0) + 1
+            ops.adam_multi(table, nchunks, self._dev_state, group["lr"], beta1, beta2, group["eps"], self.grad_scale)
+            self._dev_step = before + 1
+            self._last = (steps, [p for p, _, _, _ in items])
+            self._bump(steps, self._last[1])
         return loss
+
+    @staticmethod
+    def _bump(steps, params):
+        for s in steps:
+            s += 1
+        for p in params:        # the kernel wrote p behind autograd's back: invalidate packed copies
+            p._vcg_epoch = getattr(p, "_vcg_epoch", 0) + 1
+
+    def capture_rollback(self):
+        """step() ran under CUDA-graph capture: its kernels were recorded, not executed; undo the host bump."""
+        if self._last is not None:
+            for st in self._last[0]:
+                st -= 1
+            self._dev_step -= 1
+
+    def note_replay(self):
+        """A captured CUDA graph containing this optimiser's step was replayed: the device-side counter
+        and the weights advanced; mirror that in the host-side state (state_dict 'step', cache epochs)."""
+        if self._last is not None:
+            self._bump(*self._last)
+            self._dev_step += 1
