@@ -266,3 +266,58 @@ def test_state_dict_round_trip_and_optimizer_state(env):
     # a plain torch.optim.Adam accepts our optimizer state (same keys/shapes)
     ref_opt = torch.optim.Adam(list(m2.G.parameters()), lr=2e-4, betas=(0.5, 0.999))
     ref_opt.load_state_dict(opt["optimizer_G"])
+
+
+# ------------------------------------------------------------------------------------------------
+def test_validation_step_and_eval_mode(env):
+    """validation_step in eval() mode (stale spectral-norm sigma) against the oracle."""
+    N, plan, rp = env
+    plan.set_precision("fp32")
+    N.set_eps_source(cpu_eps_source)
+    torch.manual_seed(1234)
+    model = N.CycleVAEGAN(paired=True)
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    model.configure_optimizers(lr=2e-4)
+    model.configure_loss(**rp.DEFAULT_LAMBDAS)
+    batch = rp.synthetic_batch(1)
+    ora = rp.RefModel("cyclevaegan", paired=True, state=state)
+    ora.training = False
+    model.eval()
+    torch.manual_seed(3)
+    m = model.validation_step({k: v.cuda() for k, v in batch.items()})
+    torch.manual_seed(3)
+    with torch.no_grad():
+        (Gx, FGx, Fy, GFy, mu_x, lv_x, mu_FGx, lv_FGx, mu_y, lv_y, mu_GFy, lv_GFy, DYGx, DXFy, DXx, DYy, Gy, Fx) = \
+            ora.forward(batch["x"], batch["y"])
+        lc = rp.cycle_loss(batch["x"], batch["y"], FGx, GFy)
+        lk = rp.kl_loss(mu_x, lv_x) + rp.kl_loss(mu_FGx, lv_FGx) + rp.kl_loss(mu_y, lv_y) + rp.kl_loss(mu_GFy, lv_GFy)
+        lid = rp.identity_loss(batch["x"], batch["y"], Fx, Gy)
+        ldx = rp.gan_loss_disc(DXx, DXFy)[0]
+        ldy = rp.gan_loss_disc(DYy, DYGx)[0]
+    assert set(m) >= {"total_loss", "G_loss", "D_loss", "loss_cycle", "loss_kl", "loss_identity", "Gx", "Fy"}
+    assert m["Gx"].shape == (1, 3, 256, 256) and not m["Gx"].requires_grad
+    for k, v in (("loss_cycle", lc), ("loss_kl", lk), ("loss_identity", lid), ("D_loss", ldx + ldy)):
+        assert abs(m[k] - float(v)) <= 2e-4 * abs(float(v)), (k, m[k], float(v))
+    assert rel_l2(m["Gx"].cpu(), Gx) < 1e-5
+    N.set_eps_source(None)
+
+
+@pytest.mark.parametrize("name", ["DoubleAutoencoder", "DoubleVariationalAutoencoder"])
+def test_double_models_train_and_convert(env, name):
+    """shared-encoder pretraining models step and hand their weights to a Cycle model."""
+    N, plan, rp = env
+    plan.set_precision("bf16")
+    torch.manual_seed(11)
+    m = getattr(N, name)().cuda()
+    m.configure_optimizers(lr=2e-4)
+    m.configure_loss()
+    batch = {k: v.cuda() for k, v in rp.synthetic_batch(1).items()}
+    a = m.training_step(batch)
+    b = m.training_step(batch)
+    assert a["G_loss"] == a["G_loss"] and b["G_loss"] < a["G_loss"] * 1.5
+    v = m.validation_step(batch)
+    assert v["Gx"].shape == (1, 3, 256, 256) and v["Fy"].shape == (1, 3, 256, 256)
+    cyc = m.create_cycle_ae() if name == "DoubleAutoencoder" else m.create_cycle_vae()
+    assert torch.equal(cyc.G.encoder.state_dict()["model.0.conv.weight"], m.encoder.state_dict()["model.0.conv.weight"])
+    assert torch.equal(cyc.F.decoder.state_dict()["model.5.conv.weight"], m.decoder_A.state_dict()["model.5.conv.weight"])

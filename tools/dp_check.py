@@ -1,0 +1,82 @@
+"""Data-parallel parity on W GPUs (run under torchrun): a CycleVAEGAN step on a global batch sharded over
+the ranks must reproduce the single-GPU step on the full batch: same metrics, and the
+all-reduced flat gradient / W equal to the single-GPU gradient.  fp32 parity mode, seeded eps sliced
+from a global draw.  Prints one JSON line on rank 0."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import vcg_b200  # noqa
+from oracle import ref_port as rp
+from vcg_b200 import Networks as N
+from vcg_b200 import dist as vdist
+from vcg_b200 import plan
+
+
+def make(world_rank=None, world=1):
+    torch.manual_seed(1234)
+    m = N.CycleVAEGAN(paired=False).cuda()
+    m.configure_optimizers(lr=2e-4)
+    m.configure_loss(**rp.DEFAULT_LAMBDAS)
+    m.train()
+    return m
+
+
+def main():
+    rank, local, world = vdist.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    plan.set_precision(os.environ.get("DP_PREC", "fp32"))
+    gb = 2 * world
+    batch = rp.synthetic_batch(gb)
+    state = {"calls": 0}
+
+    def eps_global(rows):
+        def src(shape, device):
+            g = torch.Generator().manual_seed(500 + state["calls"])
+            state["calls"] += 1
+            full = torch.randn(gb, *shape[1:], generator=g)
+            return full[rows].to(device)
+        return src
+
+    # ---- data parallel
+    model = make()
+    sync = vdist.attach(model)
+    per = gb // world
+    rows = slice(rank * per, (rank + 1) * per)
+    N.set_eps_source(eps_global(rows))
+    state["calls"] = 0
+    # capture the reduced gradient right before the update
+    grabbed = {}
+    orig = model.optimizer_G.pre_step_hook
+
+    def hook(o):
+        orig(o)
+        grabbed["g"] = (o.flat_grad() * o.grad_scale).clone()
+    model.optimizer_G.pre_step_hook = hook
+    m_dp = model.training_step({"x": batch["x"][rows].cuda(), "y": batch["y"][rows].cuda()})
+    out = None
+    if rank == 0:
+        ref = make()
+        N.set_eps_source(eps_global(slice(0, gb)))
+        state["calls"] = 0
+        g1 = {}
+        ref.optimizer_G.pre_step_hook = lambda o: g1.__setitem__("g", o.flat_grad().clone())
+        m_1 = ref.training_step({"x": batch["x"].cuda(), "y": batch["y"].cuda()})
+        worst = max(abs(m_dp[k] - m_1[k]) / max(abs(m_1[k]), 1e-3) for k in m_1)
+        gerr = float((grabbed["g"] - g1["g"]).norm() / g1["g"].norm())
+        out = {"world": world, "metrics_worst_rel": worst, "grad_rel_l2": gerr, "G_loss_dp": m_dp["G_loss"],
+               "G_loss_single": m_1["G_loss"], "ok": bool(worst < 1e-4 and gerr < 1e-3)}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None and not out["ok"]:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

@@ -20,13 +20,15 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 in_stats_kernel(const T* __restrict__ y, int hw, int c, int c_pitch, int pix_per_block, double* __restrict__ acc) {
   // grid: (pixel chunks, n, channel-group chunks of 32 groups)
+  // thread layout: cgl = min(32, c/8) channel-group lanes x 256/cgl pixel lanes (all 256 threads busy for thin c)
   const int cgb = min(32, c / 8 - blockIdx.z * 32);
-  const int lanes = 256 / 32;
-  const int cg = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int cgl = c / 8 < 32 ? c / 8 : 32;
+  const int lanes = 256 / cgl;
+  const int cg = threadIdx.x % cgl, pl = threadIdx.x / cgl;
   __shared__ double sacc[32 * 16];
   for (int i = threadIdx.x; i < 32 * 16; i += 256) sacc[i] = 0.0;
   __syncthreads();
-  if (cg < cgb) {
+  if (cg < cgb && pl < lanes) {
     const int ch = (blockIdx.z * 32 + cg) * 8;
     const int p0 = blockIdx.x * pix_per_block;
     const int p1 = min(hw, p0 + pix_per_block);
@@ -148,85 +150,106 @@ struct XbArgs {
   GSrc s[3];
 };
 
-// padded coordinates t in [0, L+2p) whose reflect source is i; returns count (<=3)
-__device__ __forceinline__ int mirror_list(int i, int L, int p, int (&t)[3]) {
-  int k = 0;
-  t[k++] = i + p;
-  if (i >= 1 && i <= p) t[k++] = p - i;
-  if (i >= L - 1 - p && i <= L - 2) t[k++] = p + 2 * (L - 1) - i;
-  return k;
+// k-th padded coordinate t in [0, L+2p) whose reflect source is i (k=0 direct, 1 low mirror, 2 high mirror); -1 = none
+__device__ __forceinline__ int mirror_k(int i, int L, int p, int k) {
+  if (k == 0) return i + p;
+  if (k == 1) return (i >= 1 && i <= p) ? p - i : -1;
+  return (i >= L - 1 - p && i <= L - 2) ? p + 2 * (L - 1) - i : -1;
+}
+
+// f(th, tw) for every padded position that reflects onto (i, j); interior pixels (the vast majority) take one call
+template <typename F>
+__device__ __forceinline__ void for_mirrors(int i, int Lh, int j, int Lw, int pad, F&& f) {
+  if (pad == 0 || ((i > pad) & (i < Lh - 1 - pad) & (j > pad) & (j < Lw - 1 - pad))) { f(i + pad, j + pad); return; }
+#pragma unroll 1
+  for (int kh = 0; kh < 3; ++kh) {
+    const int th = mirror_k(i, Lh, pad, kh);
+    if (th < 0) continue;
+#pragma unroll 1
+    for (int kw = 0; kw < 3; ++kw) {
+      const int tw = mirror_k(j, Lw, pad, kw);
+      if (tw >= 0) f(th, tw);
+    }
+  }
+}
+
+template <typename T> __device__ __forceinline__ void ld2(const T* p, float& a, float& b);
+template <> __device__ __forceinline__ void ld2<float>(const float* p, float& a, float& b) {
+  const float2 v = *reinterpret_cast<const float2*>(p); a = v.x; b = v.y;
+}
+template <> __device__ __forceinline__ void ld2<__nv_bfloat16>(const __nv_bfloat16* p, float& a, float& b) {
+  const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); a = v.x; b = v.y;
 }
 
 template <typename T>
 __device__ __forceinline__ void gather_src(const GSrc& s, const XbArgs& p, int n, int h, int w, int ch, float (&g)[8]) {
   const T* dxp = static_cast<const T*>(s.dxp);
-  int th[3], tw[3];
+  const int pad = s.pad, pitch = s.c_pitch;
   if (s.mode == VCG_MODE_PLAIN) {
-    const int nh = mirror_list(h, p.h, s.pad, th), nw = mirror_list(w, p.w, s.pad, tw);
-    const int hp = p.h + 2 * s.pad, wp = p.w + 2 * s.pad;
-    for (int i = 0; i < nh; ++i)
-      for (int j = 0; j < nw; ++j) {
-        float v[8];
-        ld8<T>(dxp + ((static_cast<size_t>(n) * hp + th[i]) * wp + tw[j]) * s.c_pitch + ch, v);
+    const int wp = p.w + 2 * pad;
+    const T* base = dxp + static_cast<size_t>(n) * (p.h + 2 * pad) * wp * pitch + ch;
+    for_mirrors(h, p.h, w, p.w, pad, [&](int th, int tw) {
+      float v[8];
+      ld8<T>(base + (static_cast<size_t>(th) * wp + tw) * pitch, v);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) g[q] += v[q];
-      }
+      for (int q = 0; q < 8; ++q) g[q] += v[q];
+    });
   } else if (s.mode == VCG_MODE_SHUFFLE) {
-    const int H2 = 2 * p.h, W2 = 2 * p.w;
-    const int hp = H2 + 2 * s.pad, wp = W2 + 2 * s.pad;
+    // source channels ch..ch+7 = destination channels ch/4, ch/4+1 at the four sub-pixels (PixelShuffle inverse)
+    const int H2 = 2 * p.h, W2 = 2 * p.w, wp = W2 + 2 * pad;
+    const T* base = dxp + static_cast<size_t>(n) * (H2 + 2 * pad) * wp * pitch + (ch >> 2);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int cc = ch + q, sub = cc & 3, cd = cc >> 2;
-      const int nh = mirror_list(2 * h + (sub >> 1), H2, s.pad, th), nw = mirror_list(2 * w + (sub & 1), W2, s.pad, tw);
-      float acc = 0.f;
-      for (int i = 0; i < nh; ++i)
-        for (int j = 0; j < nw; ++j)
-          acc += Elem<T>::ld(dxp + ((static_cast<size_t>(n) * hp + th[i]) * wp + tw[j]) * s.c_pitch + cd);
-      g[q] += acc;
+    for (int sub = 0; sub < 4; ++sub) {
+      float a0 = 0.f, a1 = 0.f;
+      for_mirrors(2 * h + (sub >> 1), H2, 2 * w + (sub & 1), W2, pad, [&](int th, int tw) {
+        float x0, x1;
+        ld2<T>(base + (static_cast<size_t>(th) * wp + tw) * pitch, x0, x1);
+        a0 += x0; a1 += x1;
+      });
+      g[sub] += a0; g[sub + 4] += a1;
     }
   } else if (s.mode == VCG_MODE_UNSHUFFLE) {
-    const int Hh = p.h / 2, Wh = p.w / 2;
-    const int hp = Hh + 2 * s.pad, wp = Wh + 2 * s.pad;
+    const int Hh = p.h / 2, Wh = p.w / 2, wp = Wh + 2 * pad;
     const int sub = (h & 1) * 2 + (w & 1);
-    const int nh = mirror_list(h >> 1, Hh, s.pad, th), nw = mirror_list(w >> 1, Wh, s.pad, tw);
-    for (int i = 0; i < nh; ++i)
-      for (int j = 0; j < nw; ++j) {
-        float v[8];
-        ld8<T>(dxp + ((static_cast<size_t>(n) * hp + th[i]) * wp + tw[j]) * s.c_pitch + sub * p.c + ch, v);
+    const T* base = dxp + static_cast<size_t>(n) * (Hh + 2 * pad) * wp * pitch + sub * p.c + ch;
+    for_mirrors(h >> 1, Hh, w >> 1, Wh, pad, [&](int th, int tw) {
+      float v[8];
+      ld8<T>(base + (static_cast<size_t>(th) * wp + tw) * pitch, v);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) g[q] += v[q];
-      }
-  } else {  // PAD_S2D
-    const int nh = mirror_list(h, p.h, s.pad, th), nw = mirror_list(w, p.w, s.pad, tw);
-    const int hp = (p.h + 2 * s.pad) / 2, wp = (p.w + 2 * s.pad) / 2;
-    for (int i = 0; i < nh; ++i)
-      for (int j = 0; j < nw; ++j) {
-        const int sub = (th[i] & 1) * 2 + (tw[j] & 1);
-        float v[8];
-        ld8<T>(dxp + ((static_cast<size_t>(n) * hp + (th[i] >> 1)) * wp + (tw[j] >> 1)) * s.c_pitch + sub * p.c + ch, v);
+      for (int q = 0; q < 8; ++q) g[q] += v[q];
+    });
+  } else {  // PAD_S2D: mirrors live in the padded full-resolution domain, then map to (pixel/2, sub-pixel channel block)
+    const int hp = (p.h + 2 * pad) / 2, wp = (p.w + 2 * pad) / 2;
+    const T* base = dxp + static_cast<size_t>(n) * hp * wp * pitch + ch;
+    for_mirrors(h, p.h, w, p.w, pad, [&](int th, int tw) {
+      const int sub = (th & 1) * 2 + (tw & 1);
+      float v[8];
+      ld8<T>(base + (static_cast<size_t>(th >> 1) * wp + (tw >> 1)) * pitch + sub * p.c, v);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) g[q] += v[q];
-      }
+      for (int q = 0; q < 8; ++q) g[q] += v[q];
+    });
   }
 }
 
 // grid: (pixel chunks, n, channel-group chunks of 32); block 256 = 32 channel groups x 8 pixel lanes
 template <typename T, bool PHASE2>
-__global__ void __launch_bounds__(256)
-xform_bwd_kernel(XbArgs p, const T* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gsums_in,
+__global__ void __launch_bounds__(256, 3)
+xform_bwd_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gsums_in,
                  T* __restrict__ dy, float* __restrict__ gsums, float* __restrict__ dbias, int pix_per_block) {
   const int cgb = min(32, p.c / 8 - blockIdx.z * 32);
-  const int cg = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int cgl = p.c / 8 < 32 ? p.c / 8 : 32;          // channel-group lanes; the rest of the block strides pixels
+  const int lanes = 256 / cgl;
+  const int cg = threadIdx.x % cgl, pl = threadIdx.x / cgl;
   __shared__ float sacc[32 * 24];
   for (int i = threadIdx.x; i < 32 * 24; i += 256) sacc[i] = 0.f;
   __syncthreads();
   const int n = blockIdx.y;
-  if (cg < cgb) {
+  if (cg < cgb && pl < lanes) {
     const int ch = (blockIdx.z * 32 + cg) * 8;
     const int hw = p.h * p.w;
     const int p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
     const int wpd = p.w + 2 * p.dy_halo, hpd = p.h + 2 * p.dy_halo;
-    float s1[8] = {}, s2[8] = {}, sb[8] = {};
+    float s1[8] = {}, s2[8] = {};      // norm phase 1: sum g, sum g*zhat; otherwise s1 = bias gradient
     float mean[8], rstd[8], m1[8], m2[8];
     if (p.norm) {
       const float* m = mr + (static_cast<size_t>(n) * p.c + ch) * 2;
@@ -239,7 +262,7 @@ xform_bwd_kernel(XbArgs p, const T* __restrict__ y, const float* __restrict__ mr
         for (int j = 0; j < 8; ++j) { m1[j] = gs[2 * j] * inv; m2[j] = gs[2 * j + 1] * inv; }
       }
     }
-    for (int pp = p0 + pl; pp < p1; pp += 8) {
+    for (int pp = p0 + pl; pp < p1; pp += lanes) {
       const int h = pp / p.w, w = pp - h * p.w;
       T* dptr = dy + ((static_cast<size_t>(n) * hpd + h + p.dy_halo) * wpd + w + p.dy_halo) * p.dy_c + ch;
       float g[8], yv[8];
@@ -261,7 +284,7 @@ xform_bwd_kernel(XbArgs p, const T* __restrict__ y, const float* __restrict__ mr
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             g[j] *= act_grad(yv[j], p.act) * act_grad(yv[j], p.pre_act);
-            sb[j] += g[j];
+            s1[j] += g[j];
           }
         }
       } else {
@@ -270,7 +293,7 @@ xform_bwd_kernel(XbArgs p, const T* __restrict__ y, const float* __restrict__ mr
         for (int j = 0; j < 8; ++j) {
           const float z = (yv[j] - mean[j]) * rstd[j];
           g[j] = rstd[j] * (g[j] - m1[j] - z * m2[j]) * act_grad(yv[j], p.pre_act);
-          sb[j] += g[j];
+          s1[j] += g[j];
         }
       }
       st8<T>(dptr, g);
@@ -280,7 +303,7 @@ xform_bwd_kernel(XbArgs p, const T* __restrict__ y, const float* __restrict__ mr
       for (int j = 0; j < 8; ++j) { atomicAdd(&sacc[cg * 24 + j], s1[j]); atomicAdd(&sacc[cg * 24 + 8 + j], s2[j]); }
     } else if (dbias) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&sacc[cg * 24 + 16 + j], sb[j]);
+      for (int j = 0; j < 8; ++j) atomicAdd(&sacc[cg * 24 + 16 + j], s1[j]);
     }
   }
   __syncthreads();

@@ -45,6 +45,22 @@ def _rec_end(tok):
         _Prof.records.append((*tok, e))
 
 
+def _profiled(kind):
+    """event-time a non-GEMM wrapper when profiling is on (family = `kind`, flops field carries bytes = 0)"""
+    def deco(fn):
+        def wrapper(*a, **k):
+            if _Prof.records is None:
+                return fn(*a, **k)
+            tok = _rec(kind, 0.0, "")
+            r = fn(*a, **k)
+            _rec_end(tok)
+            return r
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
+
+
 @dataclass(frozen=True)
 class ConvSpec:
     """Geometry of one reference convolution as executed by the kernels.
@@ -113,6 +129,7 @@ class ConvSpec:
         return (self.cout_pad, self.pkh, self.kwc_pad)
 
 
+@_profiled("wpack")
 def wpack(spec: ConvSpec, w_oihw, out, transpose_flip=False):
     d = spec.wpack_desc(out.dtype, transpose_flip)
     assert w_oihw.dtype == torch.float32 and w_oihw.is_contiguous()
@@ -121,6 +138,7 @@ def wpack(spec: ConvSpec, w_oihw, out, transpose_flip=False):
     return out
 
 
+@_profiled("wunpack_grad")
 def wunpack_grad(spec: ConvSpec, dw_packed, grad_oihw, accumulate=False):
     d = spec.wpack_desc(torch.float32, False)
     assert dw_packed.dtype == torch.float32 and grad_oihw.dtype == torch.float32 and grad_oihw.is_contiguous()
@@ -177,6 +195,7 @@ def conv_wgrad(spec: ConvSpec, x_pad, dy_pad, dw_packed):
     return dw_packed
 
 
+@_profiled("in_stats")
 def in_stats(y, c, mean_rstd):
     """mean/rstd [n,c,2] of a dense NHWC tensor (fp64 accumulation).  mean_rstd: float32 [n*c*2*3]."""
     n, h, w, cp = y.shape
@@ -186,6 +205,7 @@ def in_stats(y, c, mean_rstd):
     return mean_rstd
 
 
+@_profiled("in_finalize")
 def in_finalize(sums, nc, hw, mean_rstd):
     L.check(L.load().vcg_in_finalize(L.ptr(sums), nc, hw, L.ptr(mean_rstd), L.stream_ptr()), "vcg_in_finalize")
     return mean_rstd
@@ -203,6 +223,7 @@ def xform_dst_shape(n, h, w, c, mode, pad, dst_c=None):
     return (n, hd, wd, dst_c or rup(cd, 8))
 
 
+@_profiled("xform_fwd")
 def xform_fwd(src, c, dst, mode, pad, mean_rstd=None, act=L.ACT_NONE, residual=None, res_off=0):
     n, h, w, src_c = src.shape
     d = L.XformDesc(dtype=L.dtype_code(src.dtype), n=n, h=h, w=w, c=c, src_c=src_c,
@@ -221,6 +242,7 @@ def _xb_desc(y_like_dtype, n, h, w, c, y_c, norm, act, pre_act, dy, dy_halo, nsr
                       pre_act=pre_act, dy_halo=dy_halo, dy_c=dy.shape[-1], nsrc=nsrc)
 
 
+@_profiled("xform_bwd_gather")
 def xform_bwd_gather(srcs, y, n, h, w, c, dy, dy_halo, mean_rstd=None, act=L.ACT_NONE, pre_act=L.ACT_NONE,
                      gsums=None, dbias=None):
     """srcs: list of (dxp tensor, mode, pad).  Writes g into the interior of dy (+ sums for phase 2)."""
@@ -235,6 +257,7 @@ def xform_bwd_gather(srcs, y, n, h, w, c, dy, dy_halo, mean_rstd=None, act=L.ACT
     return dy
 
 
+@_profiled("xform_bwd_norm")
 def xform_bwd_norm(y, n, h, w, c, dy, dy_halo, mean_rstd, gsums, pre_act=L.ACT_NONE, dbias=None):
     d = _xb_desc(dy.dtype, n, h, w, c, y.shape[-1], True, L.ACT_NONE, pre_act, dy, dy_halo, 0)
     L.check(L.load().vcg_xform_bwd_norm(C.byref(d), L.ptr(y), L.ptr(mean_rstd), L.ptr(gsums), L.ptr(dy), L.ptr(dbias),
@@ -242,6 +265,7 @@ def xform_bwd_norm(y, n, h, w, c, dy, dy_halo, mean_rstd, gsums, pre_act=L.ACT_N
     return dy
 
 
+@_profiled("pack_nchw")
 def pack_nchw(src, dst, halo=0):
     n, c, h, w = src.shape
     assert src.dtype == torch.float32 and src.is_contiguous()
@@ -251,6 +275,7 @@ def pack_nchw(src, dst, halo=0):
     return dst
 
 
+@_profiled("unpack_nchw")
 def unpack_nchw(src, c, dst, c_off=0):
     n, h, w, src_c = src.shape
     assert dst.dtype == torch.float32 and dst.is_contiguous() and tuple(dst.shape) == (n, c, h, w)
@@ -260,21 +285,25 @@ def unpack_nchw(src, c, dst, c_off=0):
     return dst
 
 
+@_profiled("zero_")
 def zero_(t):
     L.check(L.load().vcg_zero(L.ptr(t), t.numel() * t.element_size(), L.stream_ptr()), "vcg_zero")
     return t
 
 
+@_profiled("l1_fwd_bwd")
 def l1_fwd_bwd(a, b, out_sum, grad=None, scale=0.0):
     L.check(L.load().vcg_l1_fwd_bwd(L.ptr(a), L.ptr(b), a.numel(), scale, L.ptr(out_sum), L.ptr(grad), L.stream_ptr()),
             "vcg_l1_fwd_bwd")
 
 
+@_profiled("mse_const_fwd_bwd")
 def mse_const_fwd_bwd(d, target, out_sum, grad=None, scale=0.0):
     L.check(L.load().vcg_mse_const_fwd_bwd(L.ptr(d), d.numel(), float(target), scale, L.ptr(out_sum), L.ptr(grad),
                                            L.stream_ptr()), "vcg_mse_const_fwd_bwd")
 
 
+@_profiled("kl_fwd_bwd")
 def kl_fwd_bwd(mu, lv, out_sum, gmu=None, glv=None, scale=0.0):
     L.check(L.load().vcg_kl_fwd_bwd(L.ptr(mu), L.ptr(lv), mu.numel(), scale, L.ptr(out_sum), L.ptr(gmu), L.ptr(glv),
                                     L.stream_ptr()), "vcg_kl_fwd_bwd")
@@ -284,6 +313,7 @@ def _off(t, c_off):
     return C.c_void_p(t.data_ptr() + c_off * t.element_size())
 
 
+@_profiled("reparam_fwd")
 def reparam_fwd(mu_src, mu_off, lv_src, lv_off, eps, c, z, mu_out, lv_out, kl_sum=None):
     n, h, w, _ = mu_src.shape
     assert mu_src.dtype == torch.float32 and lv_src.dtype == torch.float32
@@ -292,6 +322,7 @@ def reparam_fwd(mu_src, mu_off, lv_src, lv_off, eps, c, z, mu_out, lv_out, kl_su
                                      L.ptr(mu_out), L.ptr(lv_out), L.ptr(kl_sum), L.stream_ptr()), "vcg_reparam_fwd")
 
 
+@_profiled("reparam_bwd")
 def reparam_bwd(mu_src, mu_off, lv_src, lv_off, eps, dz, c, dmu, dlv, gmu_ext=None, glv_ext=None, kl_scale=0.0):
     n, h, w, _ = mu_src.shape
     assert mu_src.dtype == torch.float32 and lv_src.dtype == torch.float32
@@ -301,6 +332,7 @@ def reparam_bwd(mu_src, mu_off, lv_src, lv_off, eps, dz, c, dmu, dlv, gmu_ext=No
                                      L.ptr(dlv), dlv.shape[-1], L.stream_ptr()), "vcg_reparam_bwd")
 
 
+@_profiled("dhead_fwd")
 def dhead_fwd(x, w_khwc, bias, score, wnorm2):
     n = x.shape[0]
     k = x[0].numel()
@@ -308,6 +340,7 @@ def dhead_fwd(x, w_khwc, bias, score, wnorm2):
                                    L.ptr(wnorm2), L.stream_ptr()), "vcg_dhead_fwd")
 
 
+@_profiled("dhead_bwd")
 def dhead_bwd(x, w_khwc, wnorm2, gscore, dx, dw, dbias, scratch):
     n = x.shape[0]
     k = x[0].numel()
@@ -315,6 +348,7 @@ def dhead_bwd(x, w_khwc, wnorm2, gscore, dx, dw, dbias, scratch):
                                    L.ptr(dx), L.ptr(dw), L.ptr(dbias), L.ptr(scratch), L.stream_ptr()), "vcg_dhead_bwd")
 
 
+@_profiled("adam_multi")
 def adam_multi(chunks_dev, nchunks, state_dev, lr, beta1, beta2, eps, grad_scale=1.0):
     """state_dev: float32[4] device tensor {step, lr/bc1, sqrt(bc2), -}; the call advances step by one."""
     L.check(L.load().vcg_adam_multi(L.ptr(chunks_dev), nchunks, L.ptr(state_dev), lr, beta1, beta2, eps, grad_scale,
