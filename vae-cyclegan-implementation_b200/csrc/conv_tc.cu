@@ -93,12 +93,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_per_img = p.tiles_w * p.tiles_h;
+  // contiguous chunk of tiles per CTA (m fastest): consecutive tiles share the image (statistics stay in
+  // registers until the image changes) and neighbouring input rows / the same filter tile (L2 reuse)
+  const int tiles_per_cta = (p.num_tiles + gridDim.x - 1) / gridDim.x;
+  const int tile_begin = blockIdx.x * tiles_per_cta;
+  const int tile_end = min(p.num_tiles, tile_begin + tiles_per_cta);
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
         const int img = m_tile / tiles_per_img, rem = m_tile % tiles_per_img;
         const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
@@ -122,7 +127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // ===================== MMA issuer =====================
       int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.bn);
@@ -148,11 +153,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     int as = 0; uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    // per-lane running InstanceNorm sums: lane l of this warp owns column (chunk*32 + l) of the current
+    // (image, n_tile); flushed with ONE atomic pair per column when either changes (not once per tile)
+    float run1[8], run2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) run1[i] = run2[i] = 0.f;
+    int run_img = -1, run_n0 = 0;
+    auto flush_stats = [&]() {
+      if (run_img >= 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int col = run_n0 + i * 32 + lane;
+          if (i * 32 < p.bn && col < p.cout) {
+            float* dst = p.stats_acc + (static_cast<size_t>(run_img) * p.cout + col) * 2;
+            atomicAdd(dst, run1[i]);
+            atomicAdd(dst + 1, run2[i]);
+          }
+          run1[i] = run2[i] = 0.f;
+        }
+      }
+    };
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
       const int img = m_tile / tiles_per_img, rem = m_tile % tiles_per_img;
       const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
       const int n0 = n_tile * p.bn;
+      if (p.stats && (img != run_img || n0 != run_n0)) { flush_stats(); run_img = img; run_n0 = n0; }
       int h, w; bool valid;
       if (p.flat) { const int f = w0 + row; h = f / p.wp; w = f - h * p.wp; valid = (h < p.ho) && (w < p.wo); }
       else { const int hh = row / p.tw; h = h0 + hh; w = w0 + (row - hh * p.tw);
@@ -161,7 +187,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.bn);
-      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci) {
+        const int c0 = ci * 32;
+        if (c0 >= p.bn) break;
         float v[32];
         if (p.bn - c0 >= 32) {
           uint32_t r[32];
@@ -206,12 +235,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) { const float x = valid ? v[j] : 0.f; s1[j] = x; s2[j] = x * x; }
           transposed_warp_sum32(s1, lane);
           transposed_warp_sum32(s2, lane);
-          const int col = col0 + lane;
-          if (col < p.cout) {
-            float* dst = p.stats_acc + (static_cast<size_t>(img) * p.cout + col) * 2;
-            atomicAdd(dst, s1[0]);
-            atomicAdd(dst + 1, s2[0]);
-          }
+          run1[ci] += s1[0];
+          run2[ci] += s2[0];
         }
       }
       tc_fence_before();
@@ -219,6 +244,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(tempty_bar(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+    if (p.stats) flush_stats();
   }
 
   tc_fence_before();
@@ -239,9 +265,16 @@ static void pick_box(int wo, int ho, int* tw, int* th) {
   *th = t;
 }
 
+bool vcg_conv_rows_supported(const vcg_conv_desc* d, bool has_stats);
+int vcg_conv_fwd_tc_rows(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y, int out_f32,
+                         cudaStream_t stream);
+
 int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                     float* stats, int out_f32, cudaStream_t stream) {
   const int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
+  // thin outputs on wide maps (64->3 7x7 and its twin, the data gradient of 3->64 7x7): multi-row blocks
+  // with a resident filter (conv_tc_rows.cu)
+  if (vcg_conv_rows_supported(d, d->stats && stats)) return vcg_conv_fwd_tc_rows(d, x, w, bias, y, out_f32, stream);
   VCG_REQUIRE(d->c % 8 == 0 && d->kwc_pad % 64 == 0 && d->cout_pad % 16 == 0 && d->out_c % 8 == 0,
               VCG_E_UNSUPPORTED, "conv_tc: unsupported channel geometry c=%d kwc_pad=%d cout_pad=%d cout=%d",
               d->c, d->kwc_pad, d->cout_pad, d->cout);
