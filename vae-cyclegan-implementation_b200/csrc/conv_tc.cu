@@ -17,8 +17,10 @@
 //   epilogue   = tcgen05.ld -> +bias -> ReLU/LeakyReLU -> InstanceNorm sum/sumsq (warp-shuffle
 //                transposed reduction + one atomic per column per warp) -> bf16/fp32 NHWC store.
 //
-// warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (TMEM lane
-// quadrant = warp & 3).
+// warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue (TMEM lane
+// quadrant = warp & 3; two warps per quadrant split the 32-column chunks).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -37,7 +39,7 @@ struct ConvTcArgs {
 };
 
 constexpr int kAStageBytes = 16384;  // 128 rows x 128 B
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;   // warps 0-2: TMA / MMA / TMEM alloc, 3: idle, 4-11: epilogue (2 per TMEM lane quadrant)
 
 // Sum over the 32 lanes of a warp of v[j] for each j: afterwards lane l holds column l in v[0].
 __device__ __forceinline__ void transposed_warp_sum32(float (&v)[32], int lane) {
@@ -80,7 +82,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -150,7 +152,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int quad = warp & 3;
+    // two epilogue warps per TMEM lane quadrant: warp (4+q) takes the even 32-column chunks, warp (8+q) the odd
+    // ones, so a short-K tile (epilogue-bound) drains in half the time
+    const int quad = warp & 3, half = (warp - 4) >> 2;
     const int row = quad * 32 + lane;
     int as = 0; uint32_t aphase = 0;
     // per-lane running InstanceNorm sums: lane l of this warp owns column (chunk*32 + l) of the current
@@ -164,7 +168,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int col = run_n0 + i * 32 + lane;
-          if (i * 32 < p.bn && col < p.cout) {
+          if ((i & 1) == half && i * 32 < p.bn && col < p.cout) {
             float* dst = p.stats_acc + (static_cast<size_t>(run_img) * p.cout + col) * 2;
             atomicAdd(dst, run1[i]);
             atomicAdd(dst + 1, run2[i]);
@@ -191,6 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int ci = 0; ci < 8; ++ci) {
         const int c0 = ci * 32;
         if (c0 >= p.bn) break;
+        if ((ci & 1) != half) continue;
         float v[32];
         if (p.bn - c0 >= 32) {
           uint32_t r[32];
@@ -311,7 +316,11 @@ int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const 
   a.cout = d->cout; a.out_c = d->out_c; a.act = d->act; a.stats = (d->stats && stats) ? 1 : 0;
   a.out_f32 = out_f32;
   a.bias = bias; a.stats_acc = stats; a.out = y;
-  a.idesc = umma_idesc_bf16(128, bn, 0, 0);
+  {
+    // timing experiment only (results are garbage): read both operands as MN-major to measure its smem cost
+    static const int exp_mn = (getenv("VCG_EXP_MN") && getenv("VCG_EXP_MN")[0] == '1') ? 1 : 0;
+    a.idesc = umma_idesc_bf16(128, bn, exp_mn, exp_mn);
+  }
   const int stage_bytes = kAStageBytes + bn * 128;
   int stages = (227 * 1024 - 2048) / stage_bytes;
   if (stages > 8) stages = 8;

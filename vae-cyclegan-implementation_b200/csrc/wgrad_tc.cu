@@ -68,9 +68,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   // item -> (split, m_tile, khi, jc0)
+  // (m_tile, kh, n-tile) fastest, K-split slowest: CTAs that run at the same time reduce the SAME pixel range
+  // for different filter tiles, so dY / X are read from HBM once and re-served from L2
+  const int base_items = p.m_tiles * p.kh * p.n_tiles_per_row;
   auto decode = [&](int item, int& split, int& m_tile, int& khi, int& jc0) {
-    split = item % p.splits;
-    int rest = item / p.splits;
+    split = item / base_items;
+    int rest = item - split * base_items;
     m_tile = rest % p.m_tiles;
     const int nt = rest / p.m_tiles;
     khi = nt / p.n_tiles_per_row;

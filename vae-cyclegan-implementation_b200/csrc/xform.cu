@@ -82,14 +82,14 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 xform_fwd_kernel(const T* __restrict__ src, const float* __restrict__ mr, const T* __restrict__ res,
                  T* __restrict__ dst, XfArgs p, long long total) {
-  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (idx >= total) return;
+  // grid.y = destination row (n*hd + a), grid.x covers the (pixel b, 8-channel group g) pairs of that row:
+  // one 32-bit division per thread instead of four 64-bit ones (the kernel is a byte mover)
   const int groups = p.dst_c / 8;
-  const int g = static_cast<int>(idx % groups);
-  long long t = idx / groups;
-  const int b = static_cast<int>(t % p.wd); t /= p.wd;
-  const int a = static_cast<int>(t % p.hd);
-  const int n = static_cast<int>(t / p.hd);
+  const int xi = blockIdx.x * 256 + threadIdx.x;
+  if (xi >= p.wd * groups) return;
+  const int b = xi / groups, g = xi - b * groups;
+  for (int rowi = blockIdx.y; rowi < p.n * p.hd; rowi += gridDim.y) {
+  const int n = rowi / p.hd, a = rowi - n * p.hd;
   const int cd0 = g * 8;
   float v[8];
   T* out = dst + ((static_cast<size_t>(n) * p.hd + a) * p.wd + b) * p.dst_c + cd0;
@@ -97,7 +97,7 @@ xform_fwd_kernel(const T* __restrict__ src, const float* __restrict__ mr, const 
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
     st8<T>(out, v);
-    return;
+    continue;
   }
   int sh, sw, sc0, sstride = 1;
   if (p.mode == VCG_MODE_PLAIN) {
@@ -141,6 +141,7 @@ xform_fwd_kernel(const T* __restrict__ src, const float* __restrict__ mr, const 
     }
   }
   st8<T>(out, v);
+  }
 }
 
 // ------------------------------------------------------------------ backward transform
@@ -233,7 +234,7 @@ __device__ __forceinline__ void gather_src(const GSrc& s, const XbArgs& p, int n
 
 // grid: (pixel chunks, n, channel-group chunks of 32); block 256 = 32 channel groups x 8 pixel lanes
 template <typename T, bool PHASE2>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 xform_bwd_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gsums_in,
                  T* __restrict__ dy, float* __restrict__ gsums, float* __restrict__ dbias, int pix_per_block) {
   const int cgb = min(32, p.c / 8 - blockIdx.z * 32);
@@ -262,16 +263,25 @@ xform_bwd_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y, cons
         for (int j = 0; j < 8; ++j) { m1[j] = gs[2 * j] * inv; m2[j] = gs[2 * j + 1] * inv; }
       }
     }
-    for (int pp = p0 + pl; pp < p1; pp += lanes) {
+    const bool need_y = p.norm || p.act || p.pre_act;
+    auto dy_ptr = [&](int pp) {
       const int h = pp / p.w, w = pp - h * p.w;
-      T* dptr = dy + ((static_cast<size_t>(n) * hpd + h + p.dy_halo) * wpd + w + p.dy_halo) * p.dy_c + ch;
-      float g[8], yv[8];
-      const bool need_y = p.norm || p.act || p.pre_act;
+      return dy + ((static_cast<size_t>(n) * hpd + h + p.dy_halo) * wpd + w + p.dy_halo) * p.dy_c + ch;
+    };
+    // loads of one pixel (saved output y, and either the gathered consumer gradients or phase-1's g)
+    auto load_px = [&](int pp, float (&g)[8], float (&yv)[8]) {
       if (need_y) ld8<T>(y + (static_cast<size_t>(n) * hw + pp) * p.y_c + ch, yv);
       if (!PHASE2) {
+        const int h = pp / p.w, w = pp - h * p.w;
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = 0.f;
         for (int k = 0; k < p.nsrc; ++k) gather_src<T>(p.s[k], p, n, h, w, ch, g);
+      } else {
+        ld8<T>(dy_ptr(pp), g);
+      }
+    };
+    auto finish_px = [&](int pp, float (&g)[8], float (&yv)[8]) {
+      if (!PHASE2) {
         if (p.norm) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -288,7 +298,6 @@ xform_bwd_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y, cons
           }
         }
       } else {
-        ld8<T>(dptr, g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = (yv[j] - mean[j]) * rstd[j];
@@ -296,7 +305,16 @@ xform_bwd_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y, cons
           s1[j] += g[j];
         }
       }
-      st8<T>(dptr, g);
+      st8<T>(dy_ptr(pp), g);
+    };
+    // two pixels per iteration, all loads issued before the first store: twice the bytes in flight per thread
+    for (int pp = p0 + pl; pp < p1; pp += 2 * lanes) {
+      float gA[8], yA[8], gB[8], yB[8];
+      const bool hasB = pp + lanes < p1;
+      load_px(pp, gA, yA);
+      if (hasB) load_px(pp + lanes, gB, yB);
+      finish_px(pp, gA, yA);
+      if (hasB) finish_px(pp + lanes, gB, yB);
     }
     if (!PHASE2 && p.norm) {
 #pragma unroll
@@ -430,7 +448,8 @@ extern "C" int vcg_xform_fwd(const vcg_xform_desc* d, const void* src, const flo
   }
   VCG_REQUIRE(a.cd <= d->dst_c, VCG_E_INVALID, "xform_fwd: dst_c=%d < %d", d->dst_c, a.cd);
   const long long total = static_cast<long long>(d->n) * a.hd * a.wd * (d->dst_c / 8);
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  const long long rows = static_cast<long long>(d->n) * a.hd;
+  const dim3 blocks((a.wd * (d->dst_c / 8) + 255) / 256, static_cast<unsigned>(rows < 65535 ? rows : 65535));
   if (d->dtype == VCG_F32)
     xform_fwd_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(src), mean_rstd,
                                                         static_cast<const float*>(residual), static_cast<float*>(dst), a, total);
