@@ -210,6 +210,11 @@ VCG_API int vcg_adam_multi(const vcg_adam_chunk* chunks_dev, int32_t nchunks, fl
 VCG_API int vcg_probe_tmap(const void* base, int32_t rank, const uint64_t* dims,
                            const uint64_t* strides_bytes, const uint32_t* box);
 
+/* zero only the halo ring of an NHWC buffer [n, h+2*halo, w+2*halo, c] (dY buffers: the interior is
+ * fully overwritten by vcg_xform_bwd_gather)                                                        */
+VCG_API int vcg_zero_halo(int32_t dtype, void* buf, int32_t n, int32_t h, int32_t w, int32_t c,
+                          int32_t halo, void* stream);
+
 /* utility: fill fp32 zeros (graph-capturable memset wrapper) */
 VCG_API int vcg_zero(void* p, size_t bytes, void* stream);
 

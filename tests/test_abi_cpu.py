@@ -65,4 +65,15 @@ def test_sass_is_blackwell_native(vcg):
         pytest.skip("cuobjdump unavailable")
     sass = r.stdout
     assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
-    assert " HMMA" not in sass and "HGMMA" not in sass
+    assert "HGMMA" not in sass
+    # the warp-level HMMA path is allowed only in the degenerate M=3 weight-gradient kernel (wgrad_thin.cu);
+    # every GEMM-shaped convolution must be on tcgen05 (UTCHMMA)
+    fn = None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+        elif " HMMA" in line:
+            assert fn is not None and "wgrad_thin" in fn, f"legacy HMMA in {fn}"
+    for must in ("conv_tc_kernel", "wgrad_tc_kernel", "conv_tc_rows_kernel"):
+        body = sass.split(must, 1)[1].split("Function :", 1)[0] if must in sass else ""
+        assert "UTCHMMA" in body, must

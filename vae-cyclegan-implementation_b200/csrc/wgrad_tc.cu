@@ -94,13 +94,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * stage_bytes, sb = sa + 2 * kSub;
           mbar_expect_tx(full_bar(stage), stage_bytes);
-          tma_load_4d(sa, &tmDy, full_bar(stage), m_tile * 128, w0 + p.halo, h0 + p.halo, img);
-          tma_load_4d(sa + kSub, &tmDy, full_bar(stage), m_tile * 128 + 64, w0 + p.halo, h0 + p.halo, img);
-          for (int s = 0; s < p.nsub; ++s) {
-            const int jc = jc0 + s;
-            if (p.window) tma_load_4d(sb + s * kSub, &tmX, full_bar(stage), jc * 64, w0, h0 + khi, img);
-            else { const int kwi = jc / p.cchunks, q = jc - kwi * p.cchunks;
-                   tma_load_4d(sb + s * kSub, &tmX, full_bar(stage), q * 64, w0 + kwi, h0 + khi, img); }
+          // rank-5 maps put the 64-channel block index last, so ONE box load lands all sub-boxes of an operand
+          // back to back in the MN-major layout ([block][pixel][64 ch]): 2 TMA instructions per stage, not 6
+          tma_load_5d(sa, &tmDy, full_bar(stage), 0, w0 + p.halo, h0 + p.halo, img, m_tile * 2);
+          if (p.window) {
+            for (int s = 0; s < p.nsub; ++s)
+              tma_load_4d(sb + s * kSub, &tmX, full_bar(stage), (jc0 + s) * 64, w0, h0 + khi, img);
+          } else {
+            tma_load_5d(sb, &tmX, full_bar(stage), 0, w0, h0 + khi, img, jc0);
           }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -196,7 +197,9 @@ int vcg_conv_wgrad_tc(const vcg_conv_desc* d, const void* x, const void* dy, int
   a.kb_total = d->n * a.tiles_w * a.tiles_h;
   const int sms = vcg_num_sms();
   const int base_items = a.m_tiles * d->kh * a.n_tiles_per_row;
-  int splits = (2 * sms + base_items - 1) / base_items;
+  // K splits: as many as keep the item count at or below a whole number of waves (a single extra item would
+  // add a full wave: 297 items on 148 SMs take 3 rounds, 288 take 2)
+  int splits = (2 * sms) / base_items;
   if (splits > a.kb_total / 4) splits = a.kb_total / 4;
   if (splits < 1) splits = 1;
   a.kb_per_split = (a.kb_total + splits - 1) / splits;
@@ -216,21 +219,31 @@ int vcg_conv_wgrad_tc(const vcg_conv_desc* d, const void* x, const void* dy, int
   CUtensorMap tmDy, tmX;
   const uint64_t es = 2;
   {
+    // dY as (64 ch, w, h, n, ch/64): the channel-block index is the LAST (slowest) box dimension
     const uint64_t wpd = wo + 2 * dy_halo, hpd = ho + 2 * dy_halo;
-    uint64_t dims[4] = {static_cast<uint64_t>(dy_c), wpd, hpd, static_cast<uint64_t>(d->n)};
-    uint64_t str[3] = {dy_c * es, wpd * dy_c * es, hpd * wpd * dy_c * es};
-    uint32_t box[4] = {64, static_cast<uint32_t>(a.tw), static_cast<uint32_t>(a.th), 1};
-    int rc = vcg_encode_tmap(&tmDy, dy, 4, dims, str, box, "wgrad_tc dY");
+    uint64_t dims[5] = {static_cast<uint64_t>(dy_c < 64 ? dy_c : 64), wpd, hpd, static_cast<uint64_t>(d->n),
+                        static_cast<uint64_t>((dy_c + 63) / 64)};
+    uint64_t str[4] = {dy_c * es, wpd * dy_c * es, hpd * wpd * dy_c * es, 128};
+    uint32_t box[5] = {64, static_cast<uint32_t>(a.tw), static_cast<uint32_t>(a.th), 1, 2};
+    int rc = vcg_encode_tmap(&tmDy, dy, 5, dims, str, box, "wgrad_tc dY");
     if (rc) return rc;
   }
-  {
+  if (window) {
     const uint64_t pix = d->c * es, row = d->wp * pix, img = d->hp * row;
-    uint64_t dims[4] = {window ? static_cast<uint64_t>(d->kw) * d->c : static_cast<uint64_t>(d->c),
-                        window ? static_cast<uint64_t>(wo) : static_cast<uint64_t>(d->wp),
-                        static_cast<uint64_t>(d->hp), static_cast<uint64_t>(d->n)};
+    uint64_t dims[4] = {static_cast<uint64_t>(d->kw) * d->c, static_cast<uint64_t>(wo), static_cast<uint64_t>(d->hp),
+                        static_cast<uint64_t>(d->n)};
     uint64_t str[3] = {pix, row, img};
     uint32_t box[4] = {64, static_cast<uint32_t>(a.tw), static_cast<uint32_t>(a.th), 1};
-    int rc = vcg_encode_tmap(&tmX, x, 4, dims, str, box, "wgrad_tc X");
+    int rc = vcg_encode_tmap(&tmX, x, 4, dims, str, box, "wgrad_tc X (window)");
+    if (rc) return rc;
+  } else {
+    // X as (64 elems, w positions, h, n, chunk of the (kw, c) run): chunk jc starts jc*128 B into the pixel's window
+    const uint64_t pix = d->c * es, row = d->wp * pix, img = d->hp * row;
+    uint64_t dims[5] = {64, static_cast<uint64_t>(wo), static_cast<uint64_t>(d->hp), static_cast<uint64_t>(d->n),
+                        static_cast<uint64_t>(d->kwc_pad / 64)};
+    uint64_t str[4] = {pix, row, img, 128};
+    uint32_t box[5] = {64, static_cast<uint32_t>(a.tw), static_cast<uint32_t>(a.th), 1, static_cast<uint32_t>(nsub)};
+    int rc = vcg_encode_tmap(&tmX, x, 5, dims, str, box, "wgrad_tc X");
     if (rc) return rc;
   }
   static bool attr_set = false;

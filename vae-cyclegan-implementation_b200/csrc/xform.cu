@@ -375,6 +375,28 @@ __global__ void unpack_nchw_kernel(const T* __restrict__ src, int src_c, int n, 
   dst[idx] = Elem<T>::ld(src + ((static_cast<size_t>(ni) * h + hh) * w + ww) * src_c + ch);
 }
 
+// zero only the halo ring of an NHWC buffer [n, h+2*halo, w+2*halo, c] (the interior is fully overwritten by
+// the backward transform, so clearing the whole dY buffer would double its write traffic)
+__global__ void zero_halo_kernel(uint4* __restrict__ buf, int n, int h, int w, int halo, int vec_per_px) {
+  const int hp = h + 2 * halo, wp = w + 2 * halo;
+  const int ring = hp * wp - h * w;                       // halo pixels per image
+  const long long total = static_cast<long long>(n) * ring * vec_per_px;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vec_per_px);
+    long long t = i / vec_per_px;
+    const int r = static_cast<int>(t % ring);
+    const int img = static_cast<int>(t / ring);
+    int a, b;
+    const int top = halo * wp;
+    if (r < top) { a = r / wp; b = r - a * wp; }
+    else if (r < 2 * top) { const int q = r - top; a = halo + h + q / wp; b = q % wp; }
+    else { const int q = r - 2 * top; const int row = q / (2 * halo), k = q - row * 2 * halo;
+           a = halo + row; b = k < halo ? k : w + k; }
+    buf[((static_cast<size_t>(img) * hp + a) * wp + b) * vec_per_px + v] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 __global__ void zero_kernel(float4* p, size_t n16, char* tail, size_t ntail) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -539,6 +561,21 @@ extern "C" int vcg_unpack_nchw(int32_t dtype, const void* src, int32_t src_c, in
     unpack_nchw_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), src_c, n, c, h, w,
                                                                   dst, total);
   VCG_CHECK_LAUNCH("unpack_nchw_kernel");
+  return VCG_OK;
+}
+
+extern "C" int vcg_zero_halo(int32_t dtype, void* buf, int32_t n, int32_t h, int32_t w, int32_t c, int32_t halo, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (halo <= 0) return VCG_OK;
+  const int es = dtype == VCG_F32 ? 4 : 2;
+  VCG_REQUIRE((c * es) % 16 == 0, VCG_E_UNSUPPORTED, "zero_halo: pixel size must be a multiple of 16 bytes");
+  const int vec = c * es / 16;
+  const long long total = static_cast<long long>(n) * ((h + 2 * halo) * (w + 2 * halo) - h * w) * vec;
+  long long blocks = (total + 255) / 256;
+  const long long cap = 8LL * vcg_num_sms();
+  if (blocks > cap) blocks = cap;
+  zero_halo_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<uint4*>(buf), n, h, w, halo, vec);
+  VCG_CHECK_LAUNCH("zero_halo_kernel");
   return VCG_OK;
 }
 

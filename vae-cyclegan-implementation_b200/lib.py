@@ -85,6 +85,7 @@ _SIGS = {
                                  C.c_void_p]),
     "vcg_probe_tmap": (C.c_int, [C.c_void_p, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "vcg_zero": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vcg_zero_halo": (C.c_int, [i32, C.c_void_p, i32, i32, i32, i32, i32, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
 

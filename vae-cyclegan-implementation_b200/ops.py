@@ -291,6 +291,15 @@ def zero_(t):
     return t
 
 
+@_profiled("zero_halo")
+def zero_halo_(t, halo):
+    """clear only the halo ring of an NHWC buffer [n, h+2*halo, w+2*halo, c]"""
+    n, hp, wp, c = t.shape
+    L.check(L.load().vcg_zero_halo(L.dtype_code(t.dtype), L.ptr(t), n, hp - 2 * halo, wp - 2 * halo, c, halo,
+                                   L.stream_ptr()), "vcg_zero_halo")
+    return t
+
+
 @_profiled("l1_fwd_bwd")
 def l1_fwd_bwd(a, b, out_sum, grad=None, scale=0.0):
     L.check(L.load().vcg_l1_fwd_bwd(L.ptr(a), L.ptr(b), a.numel(), scale, L.ptr(out_sum), L.ptr(grad), L.stream_ptr()),

@@ -414,7 +414,7 @@ class Plan:
                     continue          # dead branch: nothing downstream needs this layer's gradient
                 a0, spec, holder = node.out_acts[0], node.spec, node.holder
                 halo = spec.pkh - 1
-                dy = ops.zero_(torch.empty(n, a0.h + 2 * halo, a0.w + 2 * halo, spec.out_c, dtype=dtype, device=dev))
+                dy = ops.zero_halo_(torch.empty(n, a0.h + 2 * halo, a0.w + 2 * halo, spec.out_c, dtype=dtype, device=dev), halo)
                 y = run.Y[node]
                 if y.dtype != dtype:          # fp32-stored final image in bf16 mode: no norm/act there
                     y = None
