@@ -251,8 +251,9 @@ def run_ours(args):
     if rank == 0 and os.environ.get("VCG_BENCH_LAYERS"):
         with open(os.environ["VCG_BENCH_LAYERS"], "w") as fh:
             for (kind, tag), v in sorted(layers.items(), key=lambda kv: -kv[1][1]):
-                fh.write(f"{kind:11s} {tag:22s} launches/step {v[2] / args.steps:5.1f}  ms/step {v[1] / args.steps:8.3f}  "
-                         f"TFLOP/s {v[0] / max(v[1], 1e-9) / 1e9:8.1f}\n")
+                # conv families: v[0] = FLOPs -> TFLOP/s; xform families: v[0] = bytes -> TB/s (same arithmetic)
+                fh.write(f"{kind:16s} {tag:34s} launches/step {v[2] / args.steps:5.1f}  ms/step {v[1] / args.steps:8.3f}  "
+                         f"T(FLOP|B)/s {v[0] / max(v[1], 1e-9) / 1e9:8.2f}\n")
     pk = peaks()
     tc_flops = sum(fam.get(k, [0, 0, 0])[0] for k in ("conv_fwd", "conv_dgrad"))
     tc_ms = sum(fam.get(k, [0, 0, 0])[1] for k in ("conv_fwd", "conv_dgrad"))

@@ -234,7 +234,7 @@ __device__ __forceinline__ void gather_src(const GSrc& s, const XbArgs& p, int n
 
 // grid: (pixel chunks, n, channel-group chunks of 32); block 256 = 32 channel groups x 8 pixel lanes
 template <typename T, bool PHASE2>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, PHASE2 ? 2 : 3)
 xform_bwd_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gsums_in,
                  T* __restrict__ dy, float* __restrict__ gsums, float* __restrict__ dbias, int pix_per_block) {
   const int cgb = min(32, p.c / 8 - blockIdx.z * 32);
@@ -307,14 +307,22 @@ xform_bwd_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y, cons
       }
       st8<T>(dy_ptr(pp), g);
     };
-    // two pixels per iteration, all loads issued before the first store: twice the bytes in flight per thread
-    for (int pp = p0 + pl; pp < p1; pp += 2 * lanes) {
-      float gA[8], yA[8], gB[8], yB[8];
-      const bool hasB = pp + lanes < p1;
-      load_px(pp, gA, yA);
-      if (hasB) load_px(pp + lanes, gB, yB);
-      finish_px(pp, gA, yA);
-      if (hasB) finish_px(pp + lanes, gB, yB);
+    if (PHASE2) {
+      // elementwise phase: two pixels per iteration, all loads issued before the first store (more bytes in flight)
+      for (int pp = p0 + pl; pp < p1; pp += 2 * lanes) {
+        float gA[8], yA[8], gB[8], yB[8];
+        const bool hasB = pp + lanes < p1;
+        load_px(pp, gA, yA);
+        if (hasB) load_px(pp + lanes, gB, yB);
+        finish_px(pp, gA, yA);
+        if (hasB) finish_px(pp + lanes, gB, yB);
+      }
+    } else {
+      for (int pp = p0 + pl; pp < p1; pp += lanes) {
+        float g[8], yv[8];
+        load_px(pp, g, yv);
+        finish_px(pp, g, yv);
+      }
     }
     if (!PHASE2 && p.norm) {
 #pragma unroll

@@ -130,6 +130,13 @@ class ConvSpec:
 
 
 @_profiled("wpack")
+def _uses_rows_kernel(dtype, c, cout_pad, kh, kw, wo, has_stats):
+    """mirror of vcg_conv_rows_supported (csrc/conv_tc_rows.cu): which kernel a bf16 conv launch runs on"""
+    if dtype != torch.bfloat16 or has_stats or c % 64 or cout_pad > 32 or wo < 128:
+        return False
+    return kh * kw * (c // 64) * cout_pad * 128 + 4 * 16384 + 2048 <= 227 * 1024
+
+
 def wpack(spec: ConvSpec, w_oihw, out, transpose_flip=False):
     d = spec.wpack_desc(out.dtype, transpose_flip)
     assert w_oihw.dtype == torch.float32 and w_oihw.is_contiguous()
@@ -156,7 +163,9 @@ def conv_fwd(spec: ConvSpec, x_pad, w_packed, bias, y, stats_acc=None, act=L.ACT
                    stats=1 if stats_acc is not None else 0, flat=0,
                    out_f32=1 if (y.dtype == torch.float32 and x_pad.dtype != torch.float32) else 0)
     assert tuple(y.shape[:3]) == (n, hp - spec.pkh + 1, wp - spec.pkw + 1), (y.shape, x_pad.shape)
-    tok = _rec("conv_fwd", spec.flops(n, y.shape[1], y.shape[2]), f"{spec.ci}->{spec.co} k{spec.kh} @{y.shape[1]}")
+    rows = _uses_rows_kernel(x_pad.dtype, c, spec.cout_pad, spec.pkh, spec.pkw, y.shape[2], stats_acc is not None)
+    tok = _rec("conv_rows_fwd" if rows else "conv_fwd", spec.flops(n, y.shape[1], y.shape[2]),
+               f"{spec.ci}->{spec.co} k{spec.kh} @{y.shape[1]}")
     L.check(L.load().vcg_conv_fwd(C.byref(d), L.ptr(x_pad), L.ptr(w_packed), L.ptr(bias), L.ptr(y), L.ptr(stats_acc),
                                   L.stream_ptr()), "vcg_conv_fwd")
     _rec_end(tok)
@@ -171,7 +180,8 @@ def conv_dgrad(spec: ConvSpec, dy_pad, w_dgrad, dxp):
                    kwc_pad=spec.d_kwc_pad, cout=spec.cin_phys, cout_pad=spec.d_rows_pad, out_c=dxp.shape[-1],
                    act=L.ACT_NONE, stats=0, flat=1, out_f32=0)
     assert tuple(dxp.shape[:3]) == (n, hd - spec.pkh + 1, wd - spec.pkw + 1), (dxp.shape, dy_pad.shape)
-    tok = _rec("conv_dgrad", spec.flops(n, hd - 2 * (spec.pkh - 1), wd - 2 * (spec.pkw - 1)),
+    rows = _uses_rows_kernel(dy_pad.dtype, c, spec.d_rows_pad, spec.pkh, spec.pkw, wd - spec.pkw + 1, False)
+    tok = _rec("conv_rows_dgrad" if rows else "conv_dgrad", spec.flops(n, hd - 2 * (spec.pkh - 1), wd - 2 * (spec.pkw - 1)),
                f"{spec.ci}->{spec.co} k{spec.kh} @{hd - 2 * (spec.pkh - 1)}")
     L.check(L.load().vcg_conv_fwd(C.byref(d), L.ptr(dy_pad), L.ptr(w_dgrad), None, L.ptr(dxp), None, L.stream_ptr()),
             "vcg_conv_fwd(dgrad)")
@@ -223,9 +233,10 @@ def xform_dst_shape(n, h, w, c, mode, pad, dst_c=None):
     return (n, hd, wd, dst_c or rup(cd, 8))
 
 
-@_profiled("xform_fwd")
 def xform_fwd(src, c, dst, mode, pad, mean_rstd=None, act=L.ACT_NONE, residual=None, res_off=0):
     n, h, w, src_c = src.shape
+    tok = _rec("xform_fwd", float(src[..., :c].numel() * src.element_size() + dst.numel() * dst.element_size()),
+               f"c{c} {h}x{w} mode{mode} pad{pad}{' norm' if mean_rstd is not None else ''}{' res' if residual is not None else ''}")
     d = L.XformDesc(dtype=L.dtype_code(src.dtype), n=n, h=h, w=w, c=c, src_c=src_c,
                     norm=1 if mean_rstd is not None else 0, act=act, mode=mode, pad=pad, dst_c=dst.shape[-1],
                     res_hp=residual.shape[1] if residual is not None else 0,
@@ -234,6 +245,7 @@ def xform_fwd(src, c, dst, mode, pad, mean_rstd=None, act=L.ACT_NONE, residual=N
     assert tuple(dst.shape) == xform_dst_shape(n, h, w, c, mode, pad, dst.shape[-1]), (dst.shape, src.shape, mode, pad)
     L.check(L.load().vcg_xform_fwd(C.byref(d), L.ptr(src), L.ptr(mean_rstd), L.ptr(residual), L.ptr(dst), L.stream_ptr()),
             "vcg_xform_fwd")
+    _rec_end(tok)
     return dst
 
 
@@ -242,10 +254,11 @@ def _xb_desc(y_like_dtype, n, h, w, c, y_c, norm, act, pre_act, dy, dy_halo, nsr
                       pre_act=pre_act, dy_halo=dy_halo, dy_c=dy.shape[-1], nsrc=nsrc)
 
 
-@_profiled("xform_bwd_gather")
 def xform_bwd_gather(srcs, y, n, h, w, c, dy, dy_halo, mean_rstd=None, act=L.ACT_NONE, pre_act=L.ACT_NONE,
                      gsums=None, dbias=None):
     """srcs: list of (dxp tensor, mode, pad).  Writes g into the interior of dy (+ sums for phase 2)."""
+    tok = _rec("xform_bwd_gather", float(sum(t.numel() * t.element_size() for t, _, _ in srcs) + 2 * n * h * w * c * dy.element_size()),
+               f"c{c} {h}x{w} modes{[m for _, m, _ in srcs]}{' norm' if mean_rstd is not None else ''}")
     arr = (L.GSrc * max(1, len(srcs)))()
     for i, (t, mode, pad) in enumerate(srcs):
         arr[i].dxp = t.data_ptr()
@@ -254,6 +267,7 @@ def xform_bwd_gather(srcs, y, n, h, w, c, dy, dy_halo, mean_rstd=None, act=L.ACT
     d = _xb_desc(dy.dtype, n, h, w, c, y.shape[-1] if y is not None else 8, norm, act, pre_act, dy, dy_halo, len(srcs))
     L.check(L.load().vcg_xform_bwd_gather(C.byref(d), arr, L.ptr(y), L.ptr(mean_rstd), L.ptr(dy), L.ptr(gsums),
                                           L.ptr(dbias), L.stream_ptr()), "vcg_xform_bwd_gather")
+    _rec_end(tok)
     return dy
 
 
