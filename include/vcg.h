@@ -137,6 +137,7 @@ VCG_API int vcg_xform_fwd(const vcg_xform_desc* d, const void* src, const float*
 typedef struct vcg_gsrc {      /* one gradient source = padded-input gradient of a consumer conv */
   const void* dxp;             /* [n, *, *, c_pitch] in the consumer's destination domain */
   int32_t mode, pad, c_pitch;
+  int32_t folded;              /* 1: vcg_fold_halo already added the reflect halo into the interior */
 } vcg_gsrc;
 typedef struct vcg_xbwd_desc {
   int32_t dtype;
@@ -150,6 +151,12 @@ typedef struct vcg_xbwd_desc {
 VCG_API int vcg_xform_bwd_gather(const vcg_xbwd_desc* d, const vcg_gsrc* srcs, const void* y,
                          const float* mean_rstd, void* dy, float* gsums /*[n,c,2]*/,
                          float* dbias /*[c] or NULL*/, void* stream);
+/* Fold the reflect halo of a consumer's padded-input gradient into its interior, IN PLACE (adjoint of the
+ * reflect padding, F.pad(mode='reflect') backward): afterwards every activation pixel reads exactly one
+ * position of dxp.  (h, w, c) are the ACTIVATION dims as in vcg_xbwd_desc; mode/pad/c_pitch as in vcg_gsrc.
+ * Only the ring of interior pixels within `pad` of the border is touched.                                   */
+VCG_API int vcg_fold_halo(int32_t dtype, void* dxp, int32_t n, int32_t h, int32_t w, int32_t c, int32_t mode,
+                  int32_t pad, int32_t c_pitch, void* stream);
 /* phase 2 (norm only), in place on dy: v = rstd*(g - mean(g) - zhat*mean(g*zhat)) * pre_act'(y) */
 VCG_API int vcg_xform_bwd_norm(const vcg_xbwd_desc* d, const void* y, const float* mean_rstd,
                        const float* gsums, void* dy, float* dbias, void* stream);

@@ -52,12 +52,16 @@ XF_CASES = [  # (mode, pad, c, h, w, norm, act, res)
     (0, 1, 64, 16, 16, True, 0, True), (0, 1, 64, 16, 16, False, 0, False), (0, 3, 8, 32, 32, True, 1, False),
     (0, 0, 16, 16, 16, True, 2, False), (1, 1, 128, 16, 16, True, 0, False), (2, 1, 32, 32, 32, True, 0, False),
     (3, 1, 16, 32, 32, True, 2, False), (3, 1, 8, 32, 32, False, 0, False), (1, 1, 64, 8, 24, False, 1, False),
+    (0, 3, 64, 64, 48, True, 0, False), (2, 1, 64, 64, 64, True, 0, False), (1, 1, 128, 24, 40, True, 0, True),
+    (3, 1, 64, 32, 64, False, 2, False), (0, 1, 512, 16, 16, True, 0, True), (2, 1, 24, 16, 16, True, 0, False),
+    (0, 2, 8, 6, 5, False, 0, False),
 ]
 
 
+@pytest.mark.parametrize("folded", [False, True], ids=["mirrors", "folded"])
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("case", XF_CASES)
-def test_xform_fwd_bwd(K, prec, case):
+def test_xform_fwd_bwd(K, prec, case, folded):
     ops, L = K
     mode, pad, c, h, w, norm, act, res = case
     dt, n = DT[prec], 2
@@ -89,7 +93,9 @@ def test_xform_fwd_bwd(K, prec, case):
     ops.pack_nchw(G, dxp)   # G is already in the destination domain
     dy = torch.zeros(n, h + 2, w + 2, c, dtype=dt, device="cuda")
     gs = torch.zeros(n * c * 2, dtype=torch.float32, device="cuda") if norm else None
-    ops.xform_bwd_gather([(dxp, mode, pad)], src, n, h, w, c, dy, 1, mr, act, 0, gs, None)
+    if folded:      # adjoint of the reflect pad applied once, in place; the gather then takes its fast path
+        ops.fold_halo_(dxp, mode, pad, h, w, c)
+    ops.xform_bwd_gather([(dxp, mode, pad, folded)], src, n, h, w, c, dy, 1, mr, act, 0, gs, None)
     if norm:
         ops.xform_bwd_norm(src, n, h, w, c, dy, 1, mr, gs)
     got_dx = nchw(dy[:, 1:-1, 1:-1].float())

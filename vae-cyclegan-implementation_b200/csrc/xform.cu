@@ -11,6 +11,8 @@
 //
 // All kernels move 8 channels (16 B bf16 / 32 B fp32) per thread with consecutive threads on
 // consecutive channel groups, so every warp access is a contiguous 512 B / 1 KB run.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -78,78 +80,44 @@ struct XfArgs {
   int res_hp, res_wp, res_c, res_off;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-xform_fwd_kernel(const T* __restrict__ src, const float* __restrict__ mr, const T* __restrict__ res,
-                 T* __restrict__ dst, XfArgs p, long long total) {
-  // grid.y = destination row (n*hd + a), grid.x covers the (pixel b, 8-channel group g) pairs of that row:
-  // one 32-bit division per thread instead of four 64-bit ones (the kernel is a byte mover)
-  const int groups = p.dst_c / 8;
-  const int xi = blockIdx.x * 256 + threadIdx.x;
-  if (xi >= p.wd * groups) return;
-  const int b = xi / groups, g = xi - b * groups;
-  for (int rowi = blockIdx.y; rowi < p.n * p.hd; rowi += gridDim.y) {
-  const int n = rowi / p.hd, a = rowi - n * p.hd;
-  const int cd0 = g * 8;
-  float v[8];
-  T* out = dst + ((static_cast<size_t>(n) * p.hd + a) * p.wd + b) * p.dst_c + cd0;
-  if (cd0 >= p.cd) {
+// raw 8-element vectors: loads are issued into packed registers and unpacked only when consumed, so several
+// independent 16-byte loads per thread can be in flight without a float register per element
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> { uint4 r; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ void ldraw(const __nv_bfloat16* p, Raw8<__nv_bfloat16>& v) { v.r = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void ldraw(const float* p, Raw8<float>& v) {
+  v.a = *reinterpret_cast<const float4*>(p); v.b = *reinterpret_cast<const float4*>(p + 4);
+}
+__device__ __forceinline__ void unpack(const Raw8<__nv_bfloat16>& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v.r);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    st8<T>(out, v);
-    continue;
-  }
-  int sh, sw, sc0, sstride = 1;
-  if (p.mode == VCG_MODE_PLAIN) {
-    sh = reflect_idx(a - p.pad, p.h); sw = reflect_idx(b - p.pad, p.w); sc0 = cd0;
-  } else if (p.mode == VCG_MODE_SHUFFLE) {
-    const int A = reflect_idx(a - p.pad, 2 * p.h), B = reflect_idx(b - p.pad, 2 * p.w);
-    sh = A >> 1; sw = B >> 1; sc0 = cd0 * 4 + (A & 1) * 2 + (B & 1); sstride = 4;
-  } else if (p.mode == VCG_MODE_UNSHUFFLE) {
-    const int A = reflect_idx(a - p.pad, p.h / 2), B = reflect_idx(b - p.pad, p.w / 2);
-    const int sub = cd0 / p.c;
-    sh = 2 * A + (sub >> 1); sw = 2 * B + (sub & 1); sc0 = cd0 - sub * p.c;
-  } else {  // PAD_S2D
-    const int sub = cd0 / p.c;
-    sh = reflect_idx(2 * a + (sub >> 1) - p.pad, p.h); sw = reflect_idx(2 * b + (sub & 1) - p.pad, p.w);
-    sc0 = cd0 - sub * p.c;
-  }
-  const size_t spix = (static_cast<size_t>(n) * p.h + sh) * p.w + sw;
-  const T* sp = src + spix * p.src_c + sc0;
-  if (sstride == 1) ld8<T>(sp, v);
-  else {
+  for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void unpack(const Raw8<float>& v, float (&f)[8]) {
+  f[0] = v.a.x; f[1] = v.a.y; f[2] = v.a.z; f[3] = v.a.w; f[4] = v.b.x; f[5] = v.b.y; f[6] = v.b.z; f[7] = v.b.w;
+}
+
+constexpr int kXfRows = 4;   // rows per unrolled iteration: 4 independent 16-byte loads in flight per thread
+
+// per-channel statistics of the pending InstanceNorm for 8 consecutive channels: sc = rstd, sf = mean
+// (applied as (v - mean) * rstd, the reference's operation order, in both precisions)
+__device__ __forceinline__ void load_scale_shift(const float* __restrict__ m, float (&sc)[8], float (&sf)[8]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = Elem<T>::ld(sp + j * 4);
-  }
-  if (p.norm) {
-    const float* m = mr + (static_cast<size_t>(n) * p.c + sc0) * 2;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (v[j] - m[2 * j * sstride]) * m[2 * j * sstride + 1];
-  }
-  if (p.act) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], p.act);
-  }
-  if (res) {
-    const T* rp = res + ((static_cast<size_t>(n) * p.res_hp + sh + p.res_off) * p.res_wp + sw + p.res_off) * p.res_c + sc0;
-    if (sstride == 1) { float r[8]; ld8<T>(rp, r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += r[j]; }
-    else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += Elem<T>::ld(rp + j * 4);
-    }
-  }
-  st8<T>(out, v);
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(m + 4 * q);   // {mean, rstd, mean, rstd}
+    sc[2 * q] = t.y; sf[2 * q] = t.x;
+    sc[2 * q + 1] = t.w; sf[2 * q + 1] = t.z;
   }
 }
 
-// ------------------------------------------------------------------ backward transform
-struct GSrc { const void* dxp; int mode, pad, c_pitch; };
-struct XbArgs {
-  int n, h, w, c, y_c, norm, act, pre_act, dy_halo, dy_c, nsrc;
-  GSrc s[3];
-};
+template <typename T> __device__ __forceinline__ void st2(T* p, float a, float b);
+template <> __device__ __forceinline__ void st2<float>(float* p, float a, float b) {
+  *reinterpret_cast<float2*>(p) = make_float2(a, b);
+}
+template <> __device__ __forceinline__ void st2<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
 
 // k-th padded coordinate t in [0, L+2p) whose reflect source is i (k=0 direct, 1 low mirror, 2 high mirror); -1 = none
 __device__ __forceinline__ int mirror_k(int i, int L, int p, int k) {
@@ -158,10 +126,172 @@ __device__ __forceinline__ int mirror_k(int i, int L, int p, int k) {
   return (i >= L - 1 - p && i <= L - 2) ? p + 2 * (L - 1) - i : -1;
 }
 
+// Destination-driven (PLAIN / UNSHUFFLE / PAD_S2D).  grid = (x chunks of a destination row, row chunks, image);
+// a thread owns one (destination column b, 8-channel group g) and walks down the rows of its chunk: the column
+// mapping, the reflect index and the InstanceNorm scale/shift are computed once, every row costs one 16-byte load
+// (+ one for the residual) and one 16-byte store, kXfRows rows in flight.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2)
+xform_fwd_kernel(const T* __restrict__ src, const float* __restrict__ mr, const T* __restrict__ res,
+                 T* __restrict__ dst, const XfArgs p, int rows_per_block) {
+  const int groups = p.dst_c / 8;
+  const int xi = blockIdx.x * 256 + threadIdx.x;
+  if (xi >= p.wd * groups) return;
+  const int b = xi / groups, g = xi - b * groups, cd0 = g * 8;
+  const int n = blockIdx.z;
+  const int a0 = blockIdx.y * rows_per_block, a1 = min(p.hd, a0 + rows_per_block);
+  const size_t orow = static_cast<size_t>(p.wd) * p.dst_c;
+  T* out = dst + (static_cast<size_t>(n) * p.hd * p.wd + b) * p.dst_c + cd0;
+  if (cd0 >= p.cd) {     // padding channel group of the destination
+    float z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = 0.f;
+    for (int a = a0; a < a1; ++a) st8<T>(out + a * orow, z);
+    return;
+  }
+  int sub = 0, sc0 = cd0, sw;
+  if (MODE == VCG_MODE_PLAIN) sw = reflect_idx(b - p.pad, p.w);
+  else if (MODE == VCG_MODE_UNSHUFFLE) {
+    sub = cd0 / p.c; sc0 = cd0 - sub * p.c;
+    sw = 2 * reflect_idx(b - p.pad, p.w / 2) + (sub & 1);
+  } else {
+    sub = cd0 / p.c; sc0 = cd0 - sub * p.c;
+    sw = reflect_idx(2 * b + (sub & 1) - p.pad, p.w);
+  }
+  auto src_row = [&](int a) {
+    if (MODE == VCG_MODE_PLAIN) return reflect_idx(a - p.pad, p.h);
+    if (MODE == VCG_MODE_UNSHUFFLE) return 2 * reflect_idx(a - p.pad, p.h / 2) + (sub >> 1);
+    return reflect_idx(2 * a + (sub >> 1) - p.pad, p.h);
+  };
+  float sc[8], sf[8];
+  if (p.norm) load_scale_shift(mr + (static_cast<size_t>(n) * p.c + sc0) * 2, sc, sf);
+  const size_t srow = static_cast<size_t>(p.w) * p.src_c;
+  const T* sbase = src + (static_cast<size_t>(n) * p.h * p.w + sw) * p.src_c + sc0;
+  const size_t rrow = static_cast<size_t>(p.res_wp) * p.res_c;
+  const T* rbase = res ? res + ((static_cast<size_t>(n) * p.res_hp + p.res_off) * p.res_wp + sw + p.res_off) * p.res_c + sc0
+                       : nullptr;
+  for (int a = a0; a < a1; a += kXfRows) {
+    Raw8<T> vr[kXfRows], rr[kXfRows];
+    int sr[kXfRows];
+#pragma unroll
+    for (int u = 0; u < kXfRows; ++u) {
+      sr[u] = src_row(min(a + u, a1 - 1));
+      ldraw(sbase + sr[u] * srow, vr[u]);
+    }
+    if (rbase) {
+#pragma unroll
+      for (int u = 0; u < kXfRows; ++u) ldraw(rbase + sr[u] * rrow, rr[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kXfRows; ++u) {
+      if (a + u >= a1) break;
+      float v[8];
+      unpack(vr[u], v);
+      if (p.norm) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (v[j] - sf[j]) * sc[j];
+      }
+      if (p.act) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], p.act);
+      }
+      if (rbase) {
+        float r[8];
+        unpack(rr[u], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += r[j];
+      }
+      st8<T>(out + (a + u) * orow, v);
+    }
+  }
+}
+
+// PixelShuffle is source-driven: a thread reads 8 consecutive SOURCE channels (= 2 destination channels x 4
+// sub-pixels) of one source pixel with one 16-byte load and scatters four channel pairs (plus their reflect
+// mirrors) -- consecutive threads write consecutive pairs, so the stores coalesce too.
+template <typename T>
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2)
+xform_fwd_shuffle_kernel(const T* __restrict__ src, const float* __restrict__ mr, const T* __restrict__ res,
+                         T* __restrict__ dst, const XfArgs p, int rows_per_block) {
+  const int sgroups = p.c / 8;
+  const int xi = blockIdx.x * 256 + threadIdx.x;
+  if (xi >= p.w * sgroups) return;
+  const int sw = xi / sgroups, sg = xi - sw * sgroups, sc0 = sg * 8;
+  const int n = blockIdx.z;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(p.h, r0 + rows_per_block);
+  const int H2 = 2 * p.h, W2 = 2 * p.w;
+  float sc[8], sf[8];
+  if (p.norm) load_scale_shift(mr + (static_cast<size_t>(n) * p.c + sc0) * 2, sc, sf);
+  int cols[2][3];
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cols[jj][k] = mirror_k(2 * sw + jj, W2, p.pad, k);
+  const size_t srow = static_cast<size_t>(p.w) * p.src_c;
+  const T* sbase = src + (static_cast<size_t>(n) * p.h * p.w + sw) * p.src_c + sc0;
+  const size_t rrow = static_cast<size_t>(p.res_wp) * p.res_c;
+  const T* rbase = res ? res + ((static_cast<size_t>(n) * p.res_hp + p.res_off) * p.res_wp + sw + p.res_off) * p.res_c + sc0
+                       : nullptr;
+  T* obase = dst + static_cast<size_t>(n) * p.hd * p.wd * p.dst_c + sg * 2;
+  for (int sh = r0; sh < r1; sh += kXfRows) {
+    Raw8<T> vr[kXfRows], rr[kXfRows];
+#pragma unroll
+    for (int u = 0; u < kXfRows; ++u) ldraw(sbase + min(sh + u, r1 - 1) * srow, vr[u]);
+    if (rbase) {
+#pragma unroll
+      for (int u = 0; u < kXfRows; ++u) ldraw(rbase + min(sh + u, r1 - 1) * rrow, rr[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kXfRows; ++u) {
+      if (sh + u >= r1) break;
+      float v[8];
+      unpack(vr[u], v);
+      if (p.norm) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (v[j] - sf[j]) * sc[j];
+      }
+      if (p.act) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], p.act);
+      }
+      if (rbase) {
+        float r[8];
+        unpack(rr[u], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += r[j];
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int th = mirror_k(2 * (sh + u) + i, H2, p.pad, kh);
+          if (th < 0) continue;
+          T* orow = obase + static_cast<size_t>(th) * p.wd * p.dst_c;
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const int tw = cols[jj][kw];
+              if (tw >= 0) st2<T>(orow + static_cast<size_t>(tw) * p.dst_c, v[i * 2 + jj], v[4 + i * 2 + jj]);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward transform
+struct GSrc { const void* dxp; int mode, pad, c_pitch, folded; };
+struct XbArgs {
+  int n, h, w, c, y_c, norm, act, pre_act, dy_halo, dy_c, nsrc;
+  GSrc s[3];
+};
+
 // f(th, tw) for every padded position that reflects onto (i, j); interior pixels (the vast majority) take one call
 template <typename F>
-__device__ __forceinline__ void for_mirrors(int i, int Lh, int j, int Lw, int pad, F&& f) {
-  if (pad == 0 || ((i > pad) & (i < Lh - 1 - pad) & (j > pad) & (j < Lw - 1 - pad))) { f(i + pad, j + pad); return; }
+__device__ __forceinline__ void for_mirrors(int i, int Lh, int j, int Lw, int pad, bool folded, F&& f) {
+  if (pad == 0 || folded || ((i > pad) & (i < Lh - 1 - pad) & (j > pad) & (j < Lw - 1 - pad))) { f(i + pad, j + pad); return; }
 #pragma unroll 1
   for (int kh = 0; kh < 3; ++kh) {
     const int th = mirror_k(i, Lh, pad, kh);
@@ -189,7 +319,7 @@ __device__ __forceinline__ void gather_src(const GSrc& s, const XbArgs& p, int n
   if (s.mode == VCG_MODE_PLAIN) {
     const int wp = p.w + 2 * pad;
     const T* base = dxp + static_cast<size_t>(n) * (p.h + 2 * pad) * wp * pitch + ch;
-    for_mirrors(h, p.h, w, p.w, pad, [&](int th, int tw) {
+    for_mirrors(h, p.h, w, p.w, pad, s.folded != 0, [&](int th, int tw) {
       float v[8];
       ld8<T>(base + (static_cast<size_t>(th) * wp + tw) * pitch, v);
 #pragma unroll
@@ -202,7 +332,7 @@ __device__ __forceinline__ void gather_src(const GSrc& s, const XbArgs& p, int n
 #pragma unroll
     for (int sub = 0; sub < 4; ++sub) {
       float a0 = 0.f, a1 = 0.f;
-      for_mirrors(2 * h + (sub >> 1), H2, 2 * w + (sub & 1), W2, pad, [&](int th, int tw) {
+      for_mirrors(2 * h + (sub >> 1), H2, 2 * w + (sub & 1), W2, pad, s.folded != 0, [&](int th, int tw) {
         float x0, x1;
         ld2<T>(base + (static_cast<size_t>(th) * wp + tw) * pitch, x0, x1);
         a0 += x0; a1 += x1;
@@ -213,7 +343,7 @@ __device__ __forceinline__ void gather_src(const GSrc& s, const XbArgs& p, int n
     const int Hh = p.h / 2, Wh = p.w / 2, wp = Wh + 2 * pad;
     const int sub = (h & 1) * 2 + (w & 1);
     const T* base = dxp + static_cast<size_t>(n) * (Hh + 2 * pad) * wp * pitch + sub * p.c + ch;
-    for_mirrors(h >> 1, Hh, w >> 1, Wh, pad, [&](int th, int tw) {
+    for_mirrors(h >> 1, Hh, w >> 1, Wh, pad, s.folded != 0, [&](int th, int tw) {
       float v[8];
       ld8<T>(base + (static_cast<size_t>(th) * wp + tw) * pitch, v);
 #pragma unroll
@@ -222,7 +352,7 @@ __device__ __forceinline__ void gather_src(const GSrc& s, const XbArgs& p, int n
   } else {  // PAD_S2D: mirrors live in the padded full-resolution domain, then map to (pixel/2, sub-pixel channel block)
     const int hp = (p.h + 2 * pad) / 2, wp = (p.w + 2 * pad) / 2;
     const T* base = dxp + static_cast<size_t>(n) * hp * wp * pitch + ch;
-    for_mirrors(h, p.h, w, p.w, pad, [&](int th, int tw) {
+    for_mirrors(h, p.h, w, p.w, pad, s.folded != 0, [&](int th, int tw) {
       const int sub = (th & 1) * 2 + (tw & 1);
       float v[8];
       ld8<T>(base + (static_cast<size_t>(th >> 1) * wp + (tw >> 1)) * pitch + sub * p.c, v);
@@ -232,10 +362,11 @@ __device__ __forceinline__ void gather_src(const GSrc& s, const XbArgs& p, int n
   }
 }
 
+// Generic fallback (channel-group counts that are not a power of two, e.g. latent_dim 96).
 // grid: (pixel chunks, n, channel-group chunks of 32); block 256 = 32 channel groups x 8 pixel lanes
 template <typename T, bool PHASE2>
 __global__ void __launch_bounds__(256, PHASE2 ? 2 : 3)
-xform_bwd_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gsums_in,
+xform_bwd_generic_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y, const float* __restrict__ mr, const float* __restrict__ gsums_in,
                  T* __restrict__ dy, float* __restrict__ gsums, float* __restrict__ dbias, int pix_per_block) {
   const int cgb = min(32, p.c / 8 - blockIdx.z * 32);
   const int cgl = p.c / 8 < 32 ? p.c / 8 : 32;          // channel-group lanes; the rest of the block strides pixels
@@ -347,6 +478,351 @@ xform_bwd_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y, cons
   }
 }
 
+// ---- fast path (power-of-two channel-group counts: every layer of the reference networks) ----------------
+// Same grid and thread mapping as the generic kernel, but
+//  (a) the reflect halo of every consumer gradient has been folded into its interior beforehand (vcg_fold_halo),
+//      so each consumer contributes exactly ONE 16-byte load per pixel at an address that is linear in
+//      (h>>s, w>>s, h&1, w&1) -- no mode switch and no mirror loop in the hot loop;
+//  (b) kXbU pixels per thread per iteration with all their loads issued before the first use;
+//  (c) the per-(n,c) sums are reduced with warp shuffles and one shared-memory slab row per warp.
+constexpr int kXbUmax = 4;
+
+__device__ __forceinline__ bool has_mirror(int i, int L, int pad) {
+  return (i >= 1 && i <= pad) || (i >= L - 1 - pad && i <= L - 2);
+}
+
+__device__ __forceinline__ void ldraw_pairs(const __nv_bfloat16* p0, const __nv_bfloat16* p1, const __nv_bfloat16* p2,
+                                            const __nv_bfloat16* p3, Raw8<__nv_bfloat16>& v) {
+  v.r.x = *reinterpret_cast<const uint32_t*>(p0); v.r.y = *reinterpret_cast<const uint32_t*>(p1);
+  v.r.z = *reinterpret_cast<const uint32_t*>(p2); v.r.w = *reinterpret_cast<const uint32_t*>(p3);
+}
+__device__ __forceinline__ void ldraw_pairs(const float* p0, const float* p1, const float* p2, const float* p3,
+                                            Raw8<float>& v) {
+  const float2 a = *reinterpret_cast<const float2*>(p0), b = *reinterpret_cast<const float2*>(p1);
+  const float2 c = *reinterpret_cast<const float2*>(p2), d = *reinterpret_cast<const float2*>(p3);
+  v.a = make_float4(a.x, a.y, b.x, b.y); v.b = make_float4(c.x, c.y, d.x, d.y);
+}
+
+// direct-term addressing of one consumer, precomputed on the host (element offsets within one image):
+//   H = h + hoff, W = w + woff;  off = (H>>sh)*rs + (W>>sh)*cs + (H&msk)*ph + (W&msk)*pw
+// PixelShuffle consumers (shuffle=1) read four channel pairs at off, off+pitch, off+ph, off+ph+pitch.
+struct FSrc {
+  const void* base;            // first direct element of image 0 (pad offsets applied)
+  long long img_stride;
+  int hoff, woff, sh, msk, rs, cs, ph, pw, pitch, shuffle;
+};
+struct XgArgs {
+  int n, h, w, c, y_c, norm, act, pre_act, dy_halo, dy_c, nsrc;
+  FSrc s[3];
+};
+
+// f(th, tw) for the mirrored padded positions only (the direct one is excluded)
+template <typename F>
+__device__ __forceinline__ void for_mirrors_only(int i, int Lh, int j, int Lw, int pad, F&& f) {
+#pragma unroll 1
+  for (int kh = 0; kh < 3; ++kh) {
+    const int th = mirror_k(i, Lh, pad, kh);
+    if (th < 0) continue;
+#pragma unroll 1
+    for (int kw = (kh == 0 ? 1 : 0); kw < 3; ++kw) {
+      const int tw = mirror_k(j, Lw, pad, kw);
+      if (tw >= 0) f(th, tw);
+    }
+  }
+}
+
+// ---- halo fold: dxp[direct(h,w)] += sum of dxp at the padded positions that reflect onto (h,w), in place.
+// Only pixels within `pad` of the border have mirrors; the kernel enumerates exactly those:
+// border rows x all columns, then the remaining rows x border columns.
+struct FoldArgs {
+  int n, h, w, c, mode, pad, pitch;
+  int ra0, rlen0, rb0, rlen1;      // border row ranges [ra0, ra0+rlen0), [rb0, rb0+rlen1) in activation coordinates
+  int ca0, clen0, cb0, clen1;      // border column ranges
+  int total;                       // work items (pixels) per image
+};
+
+__device__ __forceinline__ int nth_outside(int r, int a0, int len0, int b0, int len1) {
+  // r-th index not inside [a0,a0+len0) or [b0,b0+len1)  (a0 < b0, ranges disjoint)
+  if (r < a0) return r;
+  r -= a0;
+  const int gap = b0 - (a0 + len0);
+  if (r < gap) return a0 + len0 + r;
+  return b0 + len1 + (r - gap);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+fold_halo_kernel(T* __restrict__ dxp, const FoldArgs p) {
+  const int groups = p.c / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= static_cast<long long>(p.total) * groups) return;
+  const int cg = static_cast<int>(idx % groups);
+  int item = static_cast<int>(idx / groups);
+  const int n = blockIdx.y, ch = cg * 8;
+  const int nbh = p.rlen0 + p.rlen1, nbw = p.clen0 + p.clen1;
+  int h, w;
+  if (item < nbh * p.w) {
+    const int r = item / p.w;
+    w = item - r * p.w;
+    h = r < p.rlen0 ? p.ra0 + r : p.rb0 + (r - p.rlen0);
+  } else {
+    item -= nbh * p.w;
+    const int r = item / nbw, ci = item - r * nbw;
+    w = ci < p.clen0 ? p.ca0 + ci : p.cb0 + (ci - p.clen0);
+    h = nth_outside(r, p.ra0, p.rlen0, p.rb0, p.rlen1);
+  }
+  const int pad = p.pad, pitch = p.pitch;
+  float m[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) m[q] = 0.f;
+  if (p.mode == VCG_MODE_PLAIN) {
+    const int wp = p.w + 2 * pad;
+    T* base = dxp + static_cast<size_t>(n) * (p.h + 2 * pad) * wp * pitch + ch;
+    for_mirrors_only(h, p.h, w, p.w, pad, [&](int th, int tw) {
+      float v[8];
+      ld8<T>(base + (static_cast<size_t>(th) * wp + tw) * pitch, v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) m[q] += v[q];
+    });
+    T* d = base + (static_cast<size_t>(h + pad) * wp + w + pad) * pitch;
+    float v[8];
+    ld8<T>(d, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] += m[q];
+    st8<T>(d, v);
+  } else if (p.mode == VCG_MODE_SHUFFLE) {
+    const int H2 = 2 * p.h, W2 = 2 * p.w, wp = W2 + 2 * pad;
+    T* base = dxp + static_cast<size_t>(n) * (H2 + 2 * pad) * wp * pitch + (ch >> 2);
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      float a0 = 0.f, a1 = 0.f;
+      const int A = 2 * h + (sub >> 1), B = 2 * w + (sub & 1);
+      for_mirrors_only(A, H2, B, W2, pad, [&](int th, int tw) {
+        float x0, x1;
+        ld2<T>(base + (static_cast<size_t>(th) * wp + tw) * pitch, x0, x1);
+        a0 += x0; a1 += x1;
+      });
+      T* d = base + (static_cast<size_t>(A + pad) * wp + B + pad) * pitch;
+      float x0, x1;
+      ld2<T>(d, x0, x1);
+      st2<T>(d, x0 + a0, x1 + a1);
+    }
+  } else if (p.mode == VCG_MODE_UNSHUFFLE) {
+    const int Hh = p.h / 2, Wh = p.w / 2, wp = Wh + 2 * pad;
+    const int sub = (h & 1) * 2 + (w & 1);
+    T* base = dxp + static_cast<size_t>(n) * (Hh + 2 * pad) * wp * pitch + sub * p.c + ch;
+    for_mirrors_only(h >> 1, Hh, w >> 1, Wh, pad, [&](int th, int tw) {
+      float v[8];
+      ld8<T>(base + (static_cast<size_t>(th) * wp + tw) * pitch, v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) m[q] += v[q];
+    });
+    T* d = base + (static_cast<size_t>((h >> 1) + pad) * wp + (w >> 1) + pad) * pitch;
+    float v[8];
+    ld8<T>(d, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] += m[q];
+    st8<T>(d, v);
+  } else {
+    const int hp = (p.h + 2 * pad) / 2, wp = (p.w + 2 * pad) / 2;
+    T* base = dxp + static_cast<size_t>(n) * hp * wp * pitch + ch;
+    for_mirrors_only(h, p.h, w, p.w, pad, [&](int th, int tw) {
+      const int sub = (th & 1) * 2 + (tw & 1);
+      float v[8];
+      ld8<T>(base + (static_cast<size_t>(th >> 1) * wp + (tw >> 1)) * pitch + sub * p.c, v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) m[q] += v[q];
+    });
+    const int th = h + pad, tw = w + pad;
+    T* d = base + (static_cast<size_t>(th >> 1) * wp + (tw >> 1)) * pitch + ((th & 1) * 2 + (tw & 1)) * p.c;
+    float v[8];
+    ld8<T>(d, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] += m[q];
+    st8<T>(d, v);
+  }
+}
+
+// Block-wide sum of r[0..NV) over the threads that share a channel group (cg = threadIdx.x % cgl, cgl | 32):
+// shuffle across the pixel lanes of each warp, one slab row per warp, then emit(cg, j, total) once per block.
+template <int NV, typename F>
+__device__ __forceinline__ void reduce_groups(float (&r)[NV], int cgl, float* sred /* [8][NV][32] */, F&& emit) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int off = 16; off >= cgl; off >>= 1) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) r[j] += __shfl_xor_sync(0xffffffffu, r[j], off);
+  }
+  if (lane < cgl) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) sred[(warp * NV + j) * 32 + lane] = r[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cgl * NV; i += 256) {
+    const int l = i % cgl, j = i / cgl;
+    float t = 0.f;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) t += sred[(wp * NV + j) * 32 + l];
+    emit(l, j, t);
+  }
+}
+
+template <typename T, int kXbU, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+xform_bwd_gather_kernel(const __grid_constant__ XgArgs p, const T* __restrict__ y, const float* __restrict__ mr,
+                        T* __restrict__ dy, float* __restrict__ gsums, float* __restrict__ dbias, int pix_per_block) {
+  __shared__ float sred[8 * 16 * 32];
+  const int cgl = p.c / 8 < 32 ? p.c / 8 : 32;     // power of two; p.c/8 is a multiple of it
+  const int lanes = 256 / cgl;
+  const int cg = threadIdx.x % cgl, pl = threadIdx.x / cgl;
+  const int n = blockIdx.y;
+  const int ch = (blockIdx.z * 32 + cg) * 8;
+  const int hw = p.h * p.w;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
+  const int wpd = p.w + 2 * p.dy_halo, hpd = p.h + 2 * p.dy_halo;
+  float s[16];      // norm: [0,8) = sum g, [8,16) = sum g*zhat; otherwise [0,8) = bias gradient
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s[j] = 0.f;
+  float sc[8], sf[8];
+  if (p.norm) load_scale_shift(mr + (static_cast<size_t>(n) * p.c + ch) * 2, sc, sf);
+  const bool need_y = p.norm || p.act || p.pre_act;
+  for (int pp = p0 + pl; pp < p1; pp += kXbU * lanes) {
+    int hh[kXbU], ww[kXbU];
+    float g[kXbU][8];
+    Raw8<T> yr[kXbU];
+#pragma unroll
+    for (int u = 0; u < kXbU; ++u) {
+      const int q = min(pp + u * lanes, p1 - 1);
+      hh[u] = q / p.w; ww[u] = q - hh[u] * p.w;
+      if (need_y) ldraw(y + (static_cast<size_t>(n) * hw + q) * p.y_c + ch, yr[u]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[u][j] = 0.f;
+    }
+#pragma unroll 1
+    for (int k = 0; k < p.nsrc; ++k) {
+      const FSrc& fs = p.s[k];
+      const T* b = static_cast<const T*>(fs.base) + static_cast<size_t>(n) * fs.img_stride;
+      Raw8<T> raw[kXbU];
+      if (!fs.shuffle) {
+        b += ch;
+#pragma unroll
+        for (int u = 0; u < kXbU; ++u) {
+          const int H = hh[u] + fs.hoff, W = ww[u] + fs.woff;
+          ldraw(b + ((H >> fs.sh) * fs.rs + (W >> fs.sh) * fs.cs + (H & fs.msk) * fs.ph + (W & fs.msk) * fs.pw), raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kXbU; ++u) {
+          float f[8];
+          unpack(raw[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[u][j] += f[j];
+        }
+      } else {
+        b += ch >> 2;
+#pragma unroll
+        for (int u = 0; u < kXbU; ++u) {
+          const T* b0 = b + (hh[u] * fs.rs + ww[u] * fs.cs);
+          ldraw_pairs(b0, b0 + fs.pitch, b0 + fs.ph, b0 + fs.ph + fs.pitch, raw[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kXbU; ++u) {
+          float f[8];
+          unpack(raw[u], f);
+#pragma unroll
+          for (int sub = 0; sub < 4; ++sub) { g[u][sub] += f[2 * sub]; g[u][sub + 4] += f[2 * sub + 1]; }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kXbU; ++u) {
+      if (pp + u * lanes >= p1) break;
+      float yv[8];
+      if (need_y) unpack(yr[u], yv);
+      if (p.norm) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = (yv[j] - sf[j]) * sc[j];
+          g[u][j] *= act_grad(z, p.act);
+          s[j] += g[u][j]; s[8 + j] = fmaf(g[u][j], z, s[8 + j]);
+        }
+      } else if (need_y) {
+        // no norm: at most one activation (fused in the conv epilogue or applied after): y or act(y) share sign
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          g[u][j] *= act_grad(yv[j], p.act) * act_grad(yv[j], p.pre_act);
+          s[j] += g[u][j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += g[u][j];
+      }
+      st8<T>(dy + ((static_cast<size_t>(n) * hpd + hh[u] + p.dy_halo) * wpd + ww[u] + p.dy_halo) * p.dy_c + ch, g[u]);
+    }
+  }
+  if (p.norm) {
+    reduce_groups<16>(s, cgl, sred, [&](int l, int j, float t) {
+      atomicAdd(gsums + (static_cast<size_t>(n) * p.c + (blockIdx.z * 32 + l) * 8 + (j & 7)) * 2 + (j >> 3), t);
+    });
+  } else if (dbias) {
+    float b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = s[j];
+    reduce_groups<8>(b, cgl, sred, [&](int l, int j, float t) { atomicAdd(dbias + (blockIdx.z * 32 + l) * 8 + j, t); });
+  }
+}
+
+// phase 2 of the InstanceNorm backward: dY = rstd * (g - mean(g) - zhat * mean(g*zhat)) * pre_act'(y), in place
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+xform_bwd_norm_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y, const float* __restrict__ mr,
+                      const float* __restrict__ gsums_in, T* __restrict__ dy, float* __restrict__ dbias, int pix_per_block) {
+  constexpr int kXbU = kXbUmax;
+  __shared__ float sred[8 * 8 * 32];
+  const int cgl = p.c / 8 < 32 ? p.c / 8 : 32;
+  const int lanes = 256 / cgl;
+  const int cg = threadIdx.x % cgl, pl = threadIdx.x / cgl;
+  const int n = blockIdx.y;
+  const int ch = (blockIdx.z * 32 + cg) * 8;
+  const int hw = p.h * p.w;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
+  const int wpd = p.w + 2 * p.dy_halo, hpd = p.h + 2 * p.dy_halo;
+  float mean[8], rstd[8], m1[8], m2[8], s[8];
+  {
+    load_scale_shift(mr + (static_cast<size_t>(n) * p.c + ch) * 2, rstd, mean);
+    const float* gs = gsums_in + (static_cast<size_t>(n) * p.c + ch) * 2;
+    const float inv = 1.f / hw;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { m1[j] = gs[2 * j] * inv; m2[j] = gs[2 * j + 1] * inv; s[j] = 0.f; }
+  }
+  for (int pp = p0 + pl; pp < p1; pp += kXbU * lanes) {
+    Raw8<T> gr[kXbU], yr[kXbU];
+    T* dp[kXbU];
+#pragma unroll
+    for (int u = 0; u < kXbU; ++u) {
+      const int q = min(pp + u * lanes, p1 - 1);
+      const int h = q / p.w, w = q - h * p.w;
+      dp[u] = dy + ((static_cast<size_t>(n) * hpd + h + p.dy_halo) * wpd + w + p.dy_halo) * p.dy_c + ch;
+      ldraw(dp[u], gr[u]);
+      ldraw(y + (static_cast<size_t>(n) * hw + q) * p.y_c + ch, yr[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kXbU; ++u) {
+      if (pp + u * lanes >= p1) break;
+      float g[8], yv[8];
+      unpack(gr[u], g);
+      unpack(yr[u], yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = (yv[j] - mean[j]) * rstd[j];
+        g[j] = rstd[j] * (g[j] - m1[j] - z * m2[j]) * act_grad(yv[j], p.pre_act);
+        s[j] += g[j];
+      }
+      st8<T>(dp[u], g);
+    }
+  }
+  if (dbias)
+    reduce_groups<8>(s, cgl, sred, [&](int l, int j, float t) { atomicAdd(dbias + (blockIdx.z * 32 + l) * 8 + j, t); });
+}
+
 // ------------------------------------------------------------------ NCHW <-> NHWC
 template <typename T>
 __global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, int h, int w, T* __restrict__ dst,
@@ -424,6 +900,18 @@ static int pix_chunk(int hw, int n, int zc) {
   return static_cast<int>(per);
 }
 
+// fast backward kernels: ~8 blocks per SM in flight over the whole launch, whole unrolled iterations per thread
+static int pix_chunk_fast(int hw, int n, int zc, int cg_total) {
+  const int cgl = cg_total < 32 ? cg_total : 32;
+  const int step = kXbUmax * (256 / cgl);                  // pixels one block covers per unrolled iteration
+  long long want = 8LL * vcg_num_sms();
+  long long per = (static_cast<long long>(hw) * n * zc + want - 1) / want;
+  if (per < 2 * step) per = 2 * step;
+  per = (per + step - 1) / step * step;
+  if (per > hw) per = hw;
+  return static_cast<int>(per);
+}
+
 extern "C" int vcg_in_finalize(const float* sums, int32_t nc, int32_t hw, float* mean_rstd, void* stream) {
   in_finalize_f_kernel<<<(nc + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(sums, nc, hw, mean_rstd);
   VCG_CHECK_LAUNCH("in_finalize_f_kernel");
@@ -477,16 +965,31 @@ extern "C" int vcg_xform_fwd(const vcg_xform_desc* d, const void* src, const flo
     default: VCG_REQUIRE(false, VCG_E_INVALID, "xform_fwd: bad mode %d", d->mode);
   }
   VCG_REQUIRE(a.cd <= d->dst_c, VCG_E_INVALID, "xform_fwd: dst_c=%d < %d", d->dst_c, a.cd);
-  const long long total = static_cast<long long>(d->n) * a.hd * a.wd * (d->dst_c / 8);
-  const long long rows = static_cast<long long>(d->n) * a.hd;
-  const dim3 blocks((a.wd * (d->dst_c / 8) + 255) / 256, static_cast<unsigned>(rows < 65535 ? rows : 65535));
-  if (d->dtype == VCG_F32)
-    xform_fwd_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(src), mean_rstd,
-                                                        static_cast<const float*>(residual), static_cast<float*>(dst), a, total);
-  else
-    xform_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), mean_rstd,
-                                                                static_cast<const __nv_bfloat16*>(residual),
-                                                                static_cast<__nv_bfloat16*>(dst), a, total);
+  VCG_REQUIRE(d->n <= 65535, VCG_E_UNSUPPORTED, "xform_fwd: n=%d", d->n);
+  VCG_REQUIRE(!d->norm || (reinterpret_cast<uintptr_t>(mean_rstd) & 15) == 0, VCG_E_INVALID, "xform_fwd: statistics must be 16-byte aligned");
+  const bool shuffle = d->mode == VCG_MODE_SHUFFLE;
+  VCG_REQUIRE(!shuffle || a.cd == d->dst_c, VCG_E_UNSUPPORTED, "xform_fwd: shuffle needs dst_c == c/4");
+  // grid: x = 256-thread chunks of one row of (column, channel-group) pairs; y = row chunks; z = image.
+  // rows per block: 8 (two unrolled batches) when that still leaves >= 4 waves of blocks, else 4
+  const int row_len = shuffle ? d->w * (d->c / 8) : a.wd * (d->dst_c / 8);
+  const int nrows = shuffle ? d->h : a.hd;
+  const int xb = (row_len + 255) / 256;
+  int rpb = 2 * kXfRows;
+  if (static_cast<long long>(xb) * ((nrows + rpb - 1) / rpb) * d->n < 32LL * vcg_num_sms()) rpb = kXfRows;
+  const dim3 blocks(xb, (nrows + rpb - 1) / rpb, d->n);
+#define VCG_XF_LAUNCH(T, KERN)                                                                                   \
+  KERN<<<blocks, 256, 0, stream>>>(static_cast<const T*>(src), mean_rstd, static_cast<const T*>(residual),       \
+                                   static_cast<T*>(dst), a, rpb)
+#define VCG_XF_MODES(T)                                                                     \
+  switch (d->mode) {                                                                        \
+    case VCG_MODE_PLAIN: VCG_XF_LAUNCH(T, (xform_fwd_kernel<T, VCG_MODE_PLAIN>)); break;     \
+    case VCG_MODE_UNSHUFFLE: VCG_XF_LAUNCH(T, (xform_fwd_kernel<T, VCG_MODE_UNSHUFFLE>)); break; \
+    case VCG_MODE_PAD_S2D: VCG_XF_LAUNCH(T, (xform_fwd_kernel<T, VCG_MODE_PAD_S2D>)); break; \
+    default: VCG_XF_LAUNCH(T, xform_fwd_shuffle_kernel<T>); break;                          \
+  }
+  if (d->dtype == VCG_F32) { VCG_XF_MODES(float) } else { VCG_XF_MODES(__nv_bfloat16) }
+#undef VCG_XF_MODES
+#undef VCG_XF_LAUNCH
   VCG_CHECK_LAUNCH("xform_fwd_kernel");
   return VCG_OK;
 }
@@ -498,6 +1001,7 @@ static int fill_xb(const vcg_xbwd_desc* d, const vcg_gsrc* srcs, XbArgs& a) {
   a.pre_act = d->pre_act; a.dy_halo = d->dy_halo; a.dy_c = d->dy_c; a.nsrc = d->nsrc;
   for (int k = 0; k < d->nsrc && srcs; ++k) {
     a.s[k].dxp = srcs[k].dxp; a.s[k].mode = srcs[k].mode; a.s[k].pad = srcs[k].pad; a.s[k].c_pitch = srcs[k].c_pitch;
+    a.s[k].folded = srcs[k].folded;
     if (srcs[k].mode == VCG_MODE_SHUFFLE) VCG_REQUIRE(d->c % 32 == 0, VCG_E_UNSUPPORTED, "xform_bwd: shuffle needs c%%32==0");
   }
   return VCG_OK;
@@ -511,15 +1015,121 @@ extern "C" int vcg_xform_bwd_gather(const vcg_xbwd_desc* d, const vcg_gsrc* srcs
   if (rc) return rc;
   VCG_REQUIRE(!d->norm || (mean_rstd && gsums), VCG_E_INVALID, "xform_bwd_gather: norm needs statistics and gsums");
   const int zc = (d->c / 8 + 31) / 32, hw = d->h * d->w;
+  const int cg_total = d->c / 8;
+  bool fast = (cg_total & (cg_total - 1)) == 0 && (!d->norm || (reinterpret_cast<uintptr_t>(mean_rstd) & 15) == 0);
+  for (int k = 0; k < d->nsrc; ++k) fast = fast && (srcs[k].pad == 0 || srcs[k].folded);
+  if (fast) {
+    XgArgs g{};
+    g.n = d->n; g.h = d->h; g.w = d->w; g.c = d->c; g.y_c = d->y_c; g.norm = d->norm; g.act = d->act;
+    g.pre_act = d->pre_act; g.dy_halo = d->dy_halo; g.dy_c = d->dy_c; g.nsrc = d->nsrc;
+    const size_t es = d->dtype == VCG_F32 ? 4 : 2;
+    for (int k = 0; k < d->nsrc; ++k) {
+      FSrc& f = g.s[k];
+      const int pad = srcs[k].pad, pitch = srcs[k].c_pitch;
+      long long first = 0;       // element offset of the direct position of activation pixel (0,0), channel 0
+      f.pitch = pitch;
+      switch (srcs[k].mode) {
+        case VCG_MODE_PLAIN: {
+          const int wp = d->w + 2 * pad;
+          first = (static_cast<long long>(pad) * wp + pad) * pitch;
+          f.rs = wp * pitch; f.cs = pitch; f.img_stride = static_cast<long long>(d->h + 2 * pad) * wp * pitch;
+          break;
+        }
+        case VCG_MODE_UNSHUFFLE: {
+          const int wp = d->w / 2 + 2 * pad;
+          first = (static_cast<long long>(pad) * wp + pad) * pitch;
+          f.sh = 1; f.msk = 1; f.rs = wp * pitch; f.cs = pitch; f.ph = 2 * d->c; f.pw = d->c;
+          f.img_stride = static_cast<long long>(d->h / 2 + 2 * pad) * wp * pitch;
+          break;
+        }
+        case VCG_MODE_PAD_S2D: {
+          const int hp = (d->h + 2 * pad) / 2, wp = (d->w + 2 * pad) / 2;
+          f.hoff = pad; f.woff = pad; f.sh = 1; f.msk = 1; f.rs = wp * pitch; f.cs = pitch; f.ph = 2 * d->c; f.pw = d->c;
+          f.img_stride = static_cast<long long>(hp) * wp * pitch;
+          break;
+        }
+        default: {
+          const int wp = 2 * d->w + 2 * pad;
+          first = (static_cast<long long>(pad) * wp + pad) * pitch;
+          f.shuffle = 1; f.rs = 2 * wp * pitch; f.cs = 2 * pitch; f.ph = wp * pitch;
+          f.img_stride = static_cast<long long>(2 * d->h + 2 * pad) * wp * pitch;
+          break;
+        }
+      }
+      VCG_REQUIRE(f.img_stride < (1LL << 31), VCG_E_UNSUPPORTED, "xform_bwd_gather: image too large for 32-bit offsets");
+      f.base = static_cast<const char*>(srcs[k].dxp) + first * es;
+    }
+    const int ppb = pix_chunk_fast(hw, d->n, zc, cg_total);
+    dim3 grid((hw + ppb - 1) / ppb, d->n, zc);
+    static const int variant = getenv("VCG_XB_VARIANT") ? atoi(getenv("VCG_XB_VARIANT")) : 0;   // tuning experiment
+#define VCG_XB_LAUNCH(T, U, MINB)                                                                              \
+  xform_bwd_gather_kernel<T, U, MINB><<<grid, 256, 0, stream>>>(g, static_cast<const T*>(y), mean_rstd,       \
+                                                                static_cast<T*>(dy), gsums, dbias, ppb)
+    if (d->dtype == VCG_F32) VCG_XB_LAUNCH(float, 2, 2);
+    else if (variant == 1) VCG_XB_LAUNCH(__nv_bfloat16, 2, 3);
+    else if (variant == 2) VCG_XB_LAUNCH(__nv_bfloat16, 2, 4);
+    else if (variant == 3) VCG_XB_LAUNCH(__nv_bfloat16, 1, 4);
+    else if (variant == 4) VCG_XB_LAUNCH(__nv_bfloat16, 4, 1);
+    else VCG_XB_LAUNCH(__nv_bfloat16, 4, 2);
+#undef VCG_XB_LAUNCH
+    VCG_CHECK_LAUNCH("xform_bwd_gather_kernel");
+    return VCG_OK;
+  }
   const int ppb = pix_chunk(hw, d->n, zc);
   dim3 grid((hw + ppb - 1) / ppb, d->n, zc);
   if (d->dtype == VCG_F32)
-    xform_bwd_kernel<float, false><<<grid, 256, 0, stream>>>(a, static_cast<const float*>(y), mean_rstd, nullptr,
-                                                             static_cast<float*>(dy), gsums, dbias, ppb);
+    xform_bwd_generic_kernel<float, false><<<grid, 256, 0, stream>>>(a, static_cast<const float*>(y), mean_rstd, nullptr,
+                                                                     static_cast<float*>(dy), gsums, dbias, ppb);
   else
-    xform_bwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(a, static_cast<const __nv_bfloat16*>(y), mean_rstd,
-                                                                     nullptr, static_cast<__nv_bfloat16*>(dy), gsums, dbias, ppb);
+    xform_bwd_generic_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(a, static_cast<const __nv_bfloat16*>(y), mean_rstd,
+                                                                             nullptr, static_cast<__nv_bfloat16*>(dy), gsums, dbias, ppb);
   VCG_CHECK_LAUNCH("xform_bwd_kernel<gather>");
+  return VCG_OK;
+}
+
+// border index ranges (activation coordinates) of one axis: indices whose reflect mirrors exist
+static void border_ranges(int mode, int L_act, int pad, int* a0, int* len0, int* b0, int* len1) {
+  int lo0, lo1, hi0, hi1;      // inclusive
+  if (mode == VCG_MODE_UNSHUFFLE) {
+    const int Lh = L_act / 2;
+    lo0 = 2; lo1 = 2 * pad + 1; hi0 = 2 * (Lh - 1 - pad); hi1 = 2 * (Lh - 2) + 1;
+  } else if (mode == VCG_MODE_SHUFFLE) {
+    const int L2 = 2 * L_act;
+    lo0 = 0; lo1 = pad >> 1; hi0 = (L2 - 1 - pad) >> 1; hi1 = (L2 - 2) >> 1;
+  } else {
+    lo0 = 1; lo1 = pad; hi0 = L_act - 1 - pad; hi1 = L_act - 2;
+  }
+  if (lo0 < 0) lo0 = 0;
+  if (hi1 > L_act - 1) hi1 = L_act - 1;
+  if (hi0 < 0) hi0 = 0;
+  if (lo1 > L_act - 1) lo1 = L_act - 1;
+  if (lo1 + 1 >= hi0) {          // ranges touch or overlap: one range
+    *a0 = lo0 < hi0 ? lo0 : hi0; *len0 = (hi1 > lo1 ? hi1 : lo1) - *a0 + 1; *b0 = *a0 + *len0; *len1 = 0;
+  } else {
+    *a0 = lo0; *len0 = lo1 - lo0 + 1; *b0 = hi0; *len1 = hi1 - hi0 + 1;
+  }
+}
+
+extern "C" int vcg_fold_halo(int32_t dtype, void* dxp, int32_t n, int32_t h, int32_t w, int32_t c, int32_t mode,
+                             int32_t pad, int32_t c_pitch, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (pad <= 0) return VCG_OK;
+  VCG_REQUIRE(c % 8 == 0 && c_pitch % 8 == 0 && n <= 65535, VCG_E_UNSUPPORTED, "fold_halo: c=%d pitch=%d n=%d", c, c_pitch, n);
+  VCG_REQUIRE(mode != VCG_MODE_SHUFFLE || c % 32 == 0, VCG_E_UNSUPPORTED, "fold_halo: shuffle needs c%%32==0");
+  const int dom_h = mode == VCG_MODE_UNSHUFFLE ? h / 2 : (mode == VCG_MODE_SHUFFLE ? 2 * h : h);
+  const int dom_w = mode == VCG_MODE_UNSHUFFLE ? w / 2 : (mode == VCG_MODE_SHUFFLE ? 2 * w : w);
+  VCG_REQUIRE(pad < dom_h && pad < dom_w, VCG_E_INVALID, "fold_halo: pad %d >= extent", pad);
+  FoldArgs a{};
+  a.n = n; a.h = h; a.w = w; a.c = c; a.mode = mode; a.pad = pad; a.pitch = c_pitch;
+  border_ranges(mode, h, pad, &a.ra0, &a.rlen0, &a.rb0, &a.rlen1);
+  border_ranges(mode, w, pad, &a.ca0, &a.clen0, &a.cb0, &a.clen1);
+  const int nbh = a.rlen0 + a.rlen1, nbw = a.clen0 + a.clen1;
+  a.total = nbh * w + (h - nbh) * nbw;
+  const long long threads = static_cast<long long>(a.total) * (c / 8);
+  dim3 grid(static_cast<unsigned>((threads + 255) / 256), n);
+  if (dtype == VCG_F32) fold_halo_kernel<float><<<grid, 256, 0, stream>>>(static_cast<float*>(dxp), a);
+  else fold_halo_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<__nv_bfloat16*>(dxp), a);
+  VCG_CHECK_LAUNCH("fold_halo_kernel");
   return VCG_OK;
 }
 
@@ -531,14 +1141,27 @@ extern "C" int vcg_xform_bwd_norm(const vcg_xbwd_desc* d, const void* y, const f
   if (rc) return rc;
   VCG_REQUIRE(d->norm && mean_rstd && gsums, VCG_E_INVALID, "xform_bwd_norm: needs norm statistics");
   const int zc = (d->c / 8 + 31) / 32, hw = d->h * d->w;
+  const int cg_total = d->c / 8;
+  if ((cg_total & (cg_total - 1)) == 0 && (reinterpret_cast<uintptr_t>(mean_rstd) & 15) == 0) {
+    const int ppb = pix_chunk_fast(hw, d->n, zc, cg_total);
+    dim3 grid((hw + ppb - 1) / ppb, d->n, zc);
+    if (d->dtype == VCG_F32)
+      xform_bwd_norm_kernel<float><<<grid, 256, 0, stream>>>(a, static_cast<const float*>(y), mean_rstd, gsums,
+                                                             static_cast<float*>(dy), dbias, ppb);
+    else
+      xform_bwd_norm_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a, static_cast<const __nv_bfloat16*>(y), mean_rstd, gsums,
+                                                                     static_cast<__nv_bfloat16*>(dy), dbias, ppb);
+    VCG_CHECK_LAUNCH("xform_bwd_norm_kernel");
+    return VCG_OK;
+  }
   const int ppb = pix_chunk(hw, d->n, zc);
   dim3 grid((hw + ppb - 1) / ppb, d->n, zc);
   if (d->dtype == VCG_F32)
-    xform_bwd_kernel<float, true><<<grid, 256, 0, stream>>>(a, static_cast<const float*>(y), mean_rstd, gsums,
-                                                            static_cast<float*>(dy), nullptr, dbias, ppb);
+    xform_bwd_generic_kernel<float, true><<<grid, 256, 0, stream>>>(a, static_cast<const float*>(y), mean_rstd, gsums,
+                                                                    static_cast<float*>(dy), nullptr, dbias, ppb);
   else
-    xform_bwd_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>(a, static_cast<const __nv_bfloat16*>(y), mean_rstd,
-                                                                    gsums, static_cast<__nv_bfloat16*>(dy), nullptr, dbias, ppb);
+    xform_bwd_generic_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>(a, static_cast<const __nv_bfloat16*>(y), mean_rstd,
+                                                                            gsums, static_cast<__nv_bfloat16*>(dy), nullptr, dbias, ppb);
   VCG_CHECK_LAUNCH("xform_bwd_kernel<norm>");
   return VCG_OK;
 }

@@ -38,7 +38,7 @@ class XformDesc(C.Structure):
 
 
 class GSrc(C.Structure):
-    _fields_ = [("dxp", C.c_void_p), ("mode", i32), ("pad", i32), ("c_pitch", i32)]
+    _fields_ = [("dxp", C.c_void_p), ("mode", i32), ("pad", i32), ("c_pitch", i32), ("folded", i32)]
 
 
 class XbwdDesc(C.Structure):
@@ -66,6 +66,7 @@ _SIGS = {
     "vcg_xform_fwd": (C.c_int, [C.POINTER(XformDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vcg_xform_bwd_gather": (C.c_int, [C.POINTER(XbwdDesc), C.POINTER(GSrc), C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vcg_fold_halo": (C.c_int, [i32, C.c_void_p, i32, i32, i32, i32, i32, i32, i32, C.c_void_p]),
     "vcg_xform_bwd_norm": (C.c_int, [C.POINTER(XbwdDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
     "vcg_pack_nchw": (C.c_int, [i32, C.c_void_p, i32, i32, i32, i32, C.c_void_p, i32, i32, C.c_void_p]),

@@ -129,7 +129,6 @@ class ConvSpec:
         return (self.cout_pad, self.pkh, self.kwc_pad)
 
 
-@_profiled("wpack")
 def _uses_rows_kernel(dtype, c, cout_pad, kh, kw, wo, has_stats):
     """mirror of vcg_conv_rows_supported (csrc/conv_tc_rows.cu): which kernel a bf16 conv launch runs on"""
     if dtype != torch.bfloat16 or has_stats or c % 64 or cout_pad > 32 or wo < 128:
@@ -137,6 +136,7 @@ def _uses_rows_kernel(dtype, c, cout_pad, kh, kw, wo, has_stats):
     return kh * kw * (c // 64) * cout_pad * 128 + 4 * 16384 + 2048 <= 227 * 1024
 
 
+@_profiled("wpack")
 def wpack(spec: ConvSpec, w_oihw, out, transpose_flip=False):
     d = spec.wpack_desc(out.dtype, transpose_flip)
     assert w_oihw.dtype == torch.float32 and w_oihw.is_contiguous()
@@ -256,13 +256,16 @@ def _xb_desc(y_like_dtype, n, h, w, c, y_c, norm, act, pre_act, dy, dy_halo, nsr
 
 def xform_bwd_gather(srcs, y, n, h, w, c, dy, dy_halo, mean_rstd=None, act=L.ACT_NONE, pre_act=L.ACT_NONE,
                      gsums=None, dbias=None):
-    """srcs: list of (dxp tensor, mode, pad).  Writes g into the interior of dy (+ sums for phase 2)."""
-    tok = _rec("xform_bwd_gather", float(sum(t.numel() * t.element_size() for t, _, _ in srcs) + 2 * n * h * w * c * dy.element_size()),
-               f"c{c} {h}x{w} modes{[m for _, m, _ in srcs]}{' norm' if mean_rstd is not None else ''}")
+    """srcs: list of (dxp tensor, mode, pad[, folded]).  Writes g into the interior of dy (+ sums for phase 2).
+    folded=True: fold_halo_ already added the reflect halo of dxp into its interior (fast kernel)."""
+    tok = _rec("xform_bwd_gather", float(sum(s[0].numel() * s[0].element_size() for s in srcs) + 2 * n * h * w * c * dy.element_size()),
+               f"c{c} {h}x{w} modes{[s[1] for s in srcs]}{' norm' if mean_rstd is not None else ''}")
     arr = (L.GSrc * max(1, len(srcs)))()
-    for i, (t, mode, pad) in enumerate(srcs):
+    for i, src in enumerate(srcs):
+        t, mode, pad = src[:3]
         arr[i].dxp = t.data_ptr()
         arr[i].mode, arr[i].pad, arr[i].c_pitch = mode, pad, t.shape[-1]
+        arr[i].folded = 1 if (len(src) > 3 and src[3]) else 0
     norm = mean_rstd is not None
     d = _xb_desc(dy.dtype, n, h, w, c, y.shape[-1] if y is not None else 8, norm, act, pre_act, dy, dy_halo, len(srcs))
     L.check(L.load().vcg_xform_bwd_gather(C.byref(d), arr, L.ptr(y), L.ptr(mean_rstd), L.ptr(dy), L.ptr(gsums),
@@ -271,11 +274,21 @@ def xform_bwd_gather(srcs, y, n, h, w, c, dy, dy_halo, mean_rstd=None, act=L.ACT
     return dy
 
 
-@_profiled("xform_bwd_norm")
+@_profiled("fold_halo")
+def fold_halo_(dxp, mode, pad, h, w, c):
+    """in place: add the reflect halo of a consumer's padded-input gradient into its interior.
+    (h, w, c) = dims of the activation the consumer reads (before its shuffle / unshuffle / s2d)."""
+    L.check(L.load().vcg_fold_halo(L.dtype_code(dxp.dtype), L.ptr(dxp), dxp.shape[0], h, w, c, mode, pad, dxp.shape[-1],
+                                   L.stream_ptr()), "vcg_fold_halo")
+    return dxp
+
+
 def xform_bwd_norm(y, n, h, w, c, dy, dy_halo, mean_rstd, gsums, pre_act=L.ACT_NONE, dbias=None):
+    tok = _rec("xform_bwd_norm", float(3 * n * h * w * c * dy.element_size()), f"c{c} {h}x{w}")
     d = _xb_desc(dy.dtype, n, h, w, c, y.shape[-1], True, L.ACT_NONE, pre_act, dy, dy_halo, 0)
     L.check(L.load().vcg_xform_bwd_norm(C.byref(d), L.ptr(y), L.ptr(mean_rstd), L.ptr(gsums), L.ptr(dy), L.ptr(dbias),
                                         L.stream_ptr()), "vcg_xform_bwd_norm")
+    _rec_end(tok)
     return dy
 
 

@@ -354,7 +354,7 @@ class Plan:
             s = [(t, L.MODE_PLAIN, 0) for t in dense.get(act.id, ())]
             for c in act.consumers:
                 if isinstance(c, ConvNode) and c in dxp:
-                    s.append((dxp[c], c.mode, c.pad))
+                    s.append((dxp[c], c.mode, c.pad, True))      # halo already folded (see conv_dgrad below)
             for p in act.passthrough:
                 s.extend(sources(p))
             return s
@@ -445,6 +445,9 @@ class Plan:
                     pc.refresh(dtype)
                     g = torch.empty_like(xp)
                     ops.conv_dgrad(spec, dy, pc.wkT, g)
+                    # adjoint of the reflect padding: fold the halo into the interior once, here, so that every
+                    # gather of this gradient (it can feed two activations through a residual) reads one position
+                    ops.fold_halo_(g, node.mode, node.pad, node.inp.h, node.inp.w, node.inp.c)
                     dxp[node] = g
         res = []
         for a, need in zip(self.inputs, need_input_grad):
