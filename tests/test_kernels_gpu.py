@@ -110,6 +110,9 @@ CONV_CASES = [  # (name, n, H, W, ci_in, co, k, wmap)
     ("s2d_img", 2, 64, 64, 3, 64, 4, 2), ("e0", 1, 32, 32, 3, 64, 7, 0), ("d5", 1, 32, 32, 64, 3, 7, 0),
     ("dU4", 1, 32, 32, 32, 64, 3, 0), ("bn256", 74, 16, 16, 64, 256, 3, 0), ("longK", 1, 16, 16, 1024, 64, 3, 0),
     ("lat", 2, 16, 16, 64, 1024, 3, 0),
+    # wide maps: thin-output forward / data-gradient shapes served by conv_tc_fold.cu (taps folded into N)
+    ("d5wide", 2, 24, 160, 64, 3, 7, 0), ("e0wide", 1, 20, 140, 3, 64, 7, 0), ("dU4wide", 1, 40, 136, 32, 64, 3, 0),
+    ("d5full", 1, 256, 256, 64, 3, 7, 0),
 ]
 
 

@@ -72,7 +72,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * p.bn) tmem_cols <<= 1;
 
@@ -92,7 +92,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   // contiguous chunk of tiles per CTA (m fastest): consecutive tiles share the image (statistics stay in
@@ -101,54 +101,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tile_begin = blockIdx.x * tiles_per_cta;
   const int tile_end = min(p.num_tiles, tile_begin + tiles_per_cta);
 
+  // Producer and MMA warps run their loops with all 32 lanes (warp-uniform control flow and values, so the
+  // compiler keeps descriptors / coordinates in uniform registers) and let ONE elected lane issue the TMA / MMA
+  // instructions: issuing from inside an `if (lane == 0)` region costs an R2UR waterfall loop per instruction.
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
-        const int img = m_tile / tiles_per_img, rem = m_tile % tiles_per_img;
-        const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
-        const int n0 = n_tile * p.bn;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          int khi, kwi, q;
-          if (p.window) { khi = kb / p.cchunks; q = kb - khi * p.cchunks; kwi = 0; }
-          else { const int per = p.kw * p.cchunks; khi = kb / per; const int r = kb - khi * per;
-                 kwi = r / p.cchunks; q = r - kwi * p.cchunks; }
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+      const int img = m_tile / tiles_per_img, rem = m_tile % tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
+      const int n0 = n_tile * p.bn;
+      int khi = 0, kwi = 0, q = 0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
+        if (elect_one_sync()) {
           mbar_expect_tx(full_bar(stage), p.a_tx_bytes + b_bytes);
           if (p.flat) tma_load_4d(sa, &tmA, full_bar(stage), q * 64, w0 + khi * p.wp + kwi, 0, img);
           else        tma_load_4d(sa, &tmA, full_bar(stage), q * 64, w0 + kwi, h0 + khi, img);
           tma_load_2d(sb, &tmB, full_bar(stage), kb * 64, n0);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+        // next (kh, kw, channel chunk): window maps fold kw into the chunk index
+        if (++q == p.cchunks) { q = 0; if (p.window || ++kwi == p.kw) { kwi = 0; ++khi; } }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
-        mbar_wait(tempty_bar(as), aphase ^ 1u);
+    // ===================== MMA issuer =====================
+    int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.bn);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.bn);
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
+        const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
+        const uint64_t ad = umma_desc_sw128(sa, 16, 1024), bd = umma_desc_sw128(sb, 16, 1024);
+        if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = umma_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t bd = umma_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, ad, bd, p.idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(empty_bar(stage));
-          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(as));
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
+      if (elect_one_sync()) umma_commit(tfull_bar(as));
+      __syncwarp();
+      if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -270,6 +272,9 @@ static void pick_box(int wo, int ho, int* tw, int* th) {
   *th = t;
 }
 
+bool vcg_conv_fold_supported(const vcg_conv_desc* d, bool has_stats);
+int vcg_conv_fwd_tc_fold(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y, int out_f32,
+                         cudaStream_t stream);
 bool vcg_conv_rows_supported(const vcg_conv_desc* d, bool has_stats);
 int vcg_conv_fwd_tc_rows(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y, int out_f32,
                          cudaStream_t stream);
@@ -277,8 +282,11 @@ int vcg_conv_fwd_tc_rows(const vcg_conv_desc* d, const void* x, const void* w, c
 int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                     float* stats, int out_f32, cudaStream_t stream) {
   const int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
-  // thin outputs on wide maps (64->3 7x7 and its twin, the data gradient of 3->64 7x7): multi-row blocks
-  // with a resident filter (conv_tc_rows.cu)
+  // thin outputs on wide maps (64->3 7x7, the data gradients of 3->64 7x7 and 32->64 3x3): horizontal taps folded
+  // into N, input rows streamed once through a ring of TMEM accumulators (conv_tc_fold.cu)
+  static const bool no_fold = getenv("VCG_NO_FOLD") && getenv("VCG_NO_FOLD")[0] == '1';      // A/B timing switch
+  if (!no_fold && vcg_conv_fold_supported(d, d->stats && stats)) return vcg_conv_fwd_tc_fold(d, x, w, bias, y, out_f32, stream);
+  // remaining thin-output shapes: multi-row blocks with a resident filter (conv_tc_rows.cu)
   if (vcg_conv_rows_supported(d, d->stats && stats)) return vcg_conv_fwd_tc_rows(d, x, w, bias, y, out_f32, stream);
   VCG_REQUIRE(d->c % 8 == 0 && d->kwc_pad % 64 == 0 && d->cout_pad % 16 == 0 && d->out_c % 8 == 0,
               VCG_E_UNSUPPORTED, "conv_tc: unsupported channel geometry c=%d kwc_pad=%d cout_pad=%d cout=%d",

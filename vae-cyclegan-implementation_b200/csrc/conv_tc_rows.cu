@@ -43,7 +43,7 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
   const uint32_t bready_bar = bar0 + 8u * (2 * S + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const uint32_t acc_cols = static_cast<uint32_t>(p.R * p.bn);
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
@@ -59,7 +59,7 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   const int blocks_per_img = p.tiles_w * p.blocks_h;
   const int per_cta = (p.num_tiles + gridDim.x - 1) / gridDim.x;
@@ -87,7 +87,8 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && tile_begin < tile_end) {
+    // warp-uniform loop, one elected lane issues (see conv_tc.cu)
+    if (tile_begin < tile_end) {
       mbar_wait(bready_bar, 0);
       int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -99,23 +100,25 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int q = 0; q < p.cchunks; ++q) {
               mbar_wait(full_bar(stage), phase);
               tc_fence_after();
-              const uint32_t sa = base + stage * kAStage;
+              const uint64_t ad = umma_desc_sw128(base + stage * kAStage, 16, 1024);
               const int r_lo = rho - (p.kh - 1) > 0 ? rho - (p.kh - 1) : 0;
               const int r_hi = rho < p.R - 1 ? rho : p.R - 1;
-              // (row outer, k inner measured faster than k outer: 2.4 vs 3.1 ms on the 64->3 7x7 layer at batch 64)
-              for (int r = r_lo; r <= r_hi; ++r) {
-                const int khi = rho - r;
-                const uint32_t sb = bres + static_cast<uint32_t>((khi * p.kw + kwi) * p.cchunks + q) * b_bytes;
-                const bool first = (khi == 0) && (kwi == 0) && (q == 0);
+              if (elect_one_sync()) {
+                for (int r = r_lo; r <= r_hi; ++r) {
+                  const int khi = rho - r;
+                  const uint64_t bd = umma_desc_sw128(bres + static_cast<uint32_t>((khi * p.kw + kwi) * p.cchunks + q) * b_bytes, 16, 1024);
+                  const bool first = (khi == 0) && (kwi == 0) && (q == 0);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d0 + static_cast<uint32_t>(r * p.bn), umma_desc_sw128(sa + k * 32, 16, 1024),
-                            umma_desc_sw128(sb + k * 32, 16, 1024), p.idesc, (first && k == 0) ? 0u : 1u);
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(d0 + static_cast<uint32_t>(r * p.bn), ad + 2 * k, bd + 2 * k, p.idesc, (first && k == 0) ? 0u : 1u);
+                }
+                umma_commit(empty_bar(stage));
               }
-              umma_commit(empty_bar(stage));
+              __syncwarp();
               if (++stage == S) { stage = 0; phase ^= 1u; }
             }
-        umma_commit(tfull_bar(as));
+        if (elect_one_sync()) umma_commit(tfull_bar(as));
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }

@@ -50,7 +50,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * bn) tmem_cols <<= 1;
 
@@ -64,7 +64,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   // item -> (split, m_tile, khi, jc0)
@@ -80,19 +80,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
     jc0 = (nt - khi * p.n_tiles_per_row) * p.nsub;
   };
 
+  // producer / MMA warps: warp-uniform loops, one elected lane issues (see conv_tc.cu)
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        int split, m_tile, khi, jc0;
-        decode(item, split, m_tile, khi, jc0);
-        const int kb_begin = split * p.kb_per_split;
-        const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          const int img = kb / tiles_per_img, rem = kb - img * tiles_per_img;
-          const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = base + stage * stage_bytes, sb = sa + 2 * kSub;
+    int stage = 0; uint32_t phase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int split, m_tile, khi, jc0;
+      decode(item, split, m_tile, khi, jc0);
+      const int kb_begin = split * p.kb_per_split;
+      const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int img = kb / tiles_per_img, rem = kb - img * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = base + stage * stage_bytes, sb = sa + 2 * kSub;
+        if (elect_one_sync()) {
           mbar_expect_tx(full_bar(stage), stage_bytes);
           // rank-5 maps put the 64-channel block index last, so ONE box load lands all sub-boxes of an operand
           // back to back in the MN-major layout ([block][pixel][64 ch]): 2 TMA instructions per stage, not 6
@@ -103,37 +104,38 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
           } else {
             tma_load_5d(sb, &tmX, full_bar(stage), 0, w0, h0 + khi, img, jc0);
           }
-          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        int split, m_tile, khi, jc0;
-        decode(item, split, m_tile, khi, jc0);
-        const int kb_begin = split * p.kb_per_split;
-        const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
-        mbar_wait(tempty_bar(as), aphase ^ 1u);
+    int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int split, m_tile, khi, jc0;
+      decode(item, split, m_tile, khi, jc0);
+      const int kb_begin = split * p.kb_per_split;
+      const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * bn);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * bn);
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = base + stage * stage_bytes, sb = sa + 2 * kSub;
+        const uint32_t sa = base + stage * stage_bytes, sb = sa + 2 * kSub;
+        const uint64_t ad = umma_desc_sw128(sa, kSub, 1024), bd = umma_desc_sw128(sb, kSub, 1024);
+        if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = umma_desc_sw128(sa + k * 2048, kSub, 1024);
-            const uint64_t bd = umma_desc_sw128(sb + k * 2048, kSub, 1024);
-            umma_bf16(d_tmem, ad, bd, p.idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)      // K step = 16 pixel rows = 2048 B (descriptor address field is in 16-byte units)
+            umma_bf16(d_tmem, ad + 128 * k, bd + 128 * k, p.idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(stage));
-          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(as));
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
+      if (elect_one_sync()) umma_commit(tfull_bar(as));
+      __syncwarp();
+      if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   } else if (warp >= 4) {
     const int quad = warp & 3;

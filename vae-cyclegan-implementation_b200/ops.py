@@ -129,11 +129,19 @@ class ConvSpec:
         return (self.cout_pad, self.pkh, self.kwc_pad)
 
 
-def _uses_rows_kernel(dtype, c, cout_pad, kh, kw, wo, has_stats):
-    """mirror of vcg_conv_rows_supported (csrc/conv_tc_rows.cu): which kernel a bf16 conv launch runs on"""
-    if dtype != torch.bfloat16 or has_stats or c % 64 or cout_pad > 32 or wo < 128:
-        return False
-    return kh * kw * (c // 64) * cout_pad * 128 + 4 * 16384 + 2048 <= 227 * 1024
+def _thin_kernel(dtype, c, cout, cout_pad, kh, kw, wo, has_stats):
+    """mirror of vcg_conv_fold_supported / vcg_conv_rows_supported (csrc/conv_tc_fold.cu, conv_tc_rows.cu): which
+    kernel a bf16 conv launch runs on ('fold', 'rows' or '' = conv_tc_kernel); used only to tag profiling records"""
+    if dtype != torch.bfloat16 or has_stats or c % 64:
+        return ""
+    co8 = rup(cout, 8)
+    bn = rup(kw * co8, 16)
+    if cout <= 8 and wo >= 64 and kw in (2, 3, 7) and co8 <= cout_pad and bn <= 256 and min(8, 512 // bn) >= kh + 1 and \
+            kh * (c // 64) * bn * 128 + 2 * kw * ((cout + 3) // 4) * 2048 + 2048 + 3 * 16384 <= 227 * 1024:
+        return "fold"
+    if cout_pad <= 32 and wo >= 128 and kh * kw * (c // 64) * cout_pad * 128 + 4 * 16384 + 2048 <= 227 * 1024:
+        return "rows"
+    return ""
 
 
 @_profiled("wpack")
@@ -163,8 +171,8 @@ def conv_fwd(spec: ConvSpec, x_pad, w_packed, bias, y, stats_acc=None, act=L.ACT
                    stats=1 if stats_acc is not None else 0, flat=0,
                    out_f32=1 if (y.dtype == torch.float32 and x_pad.dtype != torch.float32) else 0)
     assert tuple(y.shape[:3]) == (n, hp - spec.pkh + 1, wp - spec.pkw + 1), (y.shape, x_pad.shape)
-    rows = _uses_rows_kernel(x_pad.dtype, c, spec.cout_pad, spec.pkh, spec.pkw, y.shape[2], stats_acc is not None)
-    tok = _rec("conv_rows_fwd" if rows else "conv_fwd", spec.flops(n, y.shape[1], y.shape[2]),
+    thin = _thin_kernel(x_pad.dtype, c, spec.co, spec.cout_pad, spec.pkh, spec.pkw, y.shape[2], stats_acc is not None)
+    tok = _rec(f"conv_{thin}_fwd" if thin else "conv_fwd", spec.flops(n, y.shape[1], y.shape[2]),
                f"{spec.ci}->{spec.co} k{spec.kh} @{y.shape[1]}")
     L.check(L.load().vcg_conv_fwd(C.byref(d), L.ptr(x_pad), L.ptr(w_packed), L.ptr(bias), L.ptr(y), L.ptr(stats_acc),
                                   L.stream_ptr()), "vcg_conv_fwd")
@@ -176,12 +184,15 @@ def conv_dgrad(spec: ConvSpec, dy_pad, w_dgrad, dxp):
     """dxp[n,hp,wp,cin_phys] = full correlation of the zero-haloed dy with the flipped filter."""
     n, hd, wd, c = dy_pad.shape
     assert c == spec.out_c
+    # logical rows of the data-gradient GEMM: the padding channels of a 3-channel image input have all-zero filter
+    # rows, so their gradient is written as literal zeros instead of being computed
+    d_cout = spec.ci if (spec.wmap == L.WMAP_PLAIN and spec.ci < spec.cin_phys) else spec.cin_phys
     d = L.ConvDesc(dtype=L.dtype_code(dy_pad.dtype), n=n, hp=hd, wp=wd, c=c, kh=spec.pkh, kw=spec.pkw,
-                   kwc_pad=spec.d_kwc_pad, cout=spec.cin_phys, cout_pad=spec.d_rows_pad, out_c=dxp.shape[-1],
+                   kwc_pad=spec.d_kwc_pad, cout=d_cout, cout_pad=spec.d_rows_pad, out_c=dxp.shape[-1],
                    act=L.ACT_NONE, stats=0, flat=1, out_f32=0)
     assert tuple(dxp.shape[:3]) == (n, hd - spec.pkh + 1, wd - spec.pkw + 1), (dxp.shape, dy_pad.shape)
-    rows = _uses_rows_kernel(dy_pad.dtype, c, spec.d_rows_pad, spec.pkh, spec.pkw, wd - spec.pkw + 1, False)
-    tok = _rec("conv_rows_dgrad" if rows else "conv_dgrad", spec.flops(n, hd - 2 * (spec.pkh - 1), wd - 2 * (spec.pkw - 1)),
+    thin = _thin_kernel(dy_pad.dtype, c, d_cout, spec.d_rows_pad, spec.pkh, spec.pkw, wd - spec.pkw + 1, False)
+    tok = _rec(f"conv_{thin}_dgrad" if thin else "conv_dgrad", spec.flops(n, hd - 2 * (spec.pkh - 1), wd - 2 * (spec.pkw - 1)),
                f"{spec.ci}->{spec.co} k{spec.kh} @{hd - 2 * (spec.pkh - 1)}")
     L.check(L.load().vcg_conv_fwd(C.byref(d), L.ptr(dy_pad), L.ptr(w_dgrad), None, L.ptr(dxp), None, L.stream_ptr()),
             "vcg_conv_fwd(dgrad)")
