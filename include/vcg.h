@@ -51,6 +51,27 @@ VCG_API const char* vcg_last_error(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
 VCG_API long long vcg_launch_count(void);
 
+/* Multi-tensor variants: ONE launch packs (both layouts) or unpacks every filter of a network.
+ * The caller fills d / pointers / accumulate for each job, runs vcg_wjob_plan on the HOST array (it assigns
+ * the tile ranges), copies the array to the device and passes the device pointer.  Packed buffers must be
+ * zero-initialised once (padding rows / columns are never written).  vcg_wunpack_multi re-zeroes the
+ * fp32 accumulators it reads, so the weight-gradient GEMMs can keep accumulating into them.            */
+typedef struct vcg_wjob {
+  int32_t co, ci, kh, kw, wmap, c_phys, co_phys, rows_pad, pkh, pkw, kwc_pad, transpose_flip; /* as vcg_wpack_desc minus dtype */
+  float* oihw;               /* pack: fp32 OIHW master (read); unpack: OIHW gradient (written) */
+  void* packed;              /* forward layout [rows_pad][pkh][kwc_pad] */
+  void* packed_t;            /* pack only: data-gradient layout [rup16(c_phys)][pkh][t_kwc_pad] or NULL */
+  int32_t t_kwc_pad;
+  int32_t accumulate;        /* unpack: grad += */
+  int32_t co_t, tiles_ci, tile0, ntiles;   /* filled by vcg_wjob_plan */
+} vcg_wjob;
+VCG_API int vcg_wjob_plan(vcg_wjob* jobs_host, int32_t njobs, int32_t* total_tiles);
+VCG_API int vcg_wpack_multi(int32_t dtype, const vcg_wjob* jobs_dev, int32_t njobs, int32_t total_tiles, void* stream);
+VCG_API int vcg_wunpack_multi(const vcg_wjob* jobs_dev, int32_t njobs, int32_t total_tiles, void* stream);
+/* dst[i] += src[i]; src[i] = 0 for every job (bias-gradient accumulators -> .grad); jobs: device array */
+typedef struct vcg_vecjob { float* src; float* dst; int32_t n, pad; } vcg_vecjob;
+VCG_API int vcg_vecflush_multi(const vcg_vecjob* jobs_dev, int32_t njobs, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Convolution as implicit GEMM.  Replaces F.pad(reflect)+F.conv2d issued by every
  * nn.Conv2d(padding_mode='reflect') (Networks.py:60,87,101,104,122,136,145;

@@ -203,6 +203,50 @@ def test_conv_layer_fwd_bwd(K, prec, case):
 
 
 # --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_wpack_multi(K, prec):
+    """multi-tensor filter pack (both layouts) / gradient unpack against the per-filter kernels"""
+    ops, L = K
+    dt = DT[prec]
+    specs = [ops.ConvSpec(128, 64, 3, 3), ops.ConvSpec(64, 128, 3, 3, L.WMAP_UNSHUFFLE, 128),
+             ops.ConvSpec(128, 64, 4, 4, L.WMAP_S2D, 256), ops.ConvSpec(64, 3, 7, 7, L.WMAP_PLAIN, 8),
+             ops.ConvSpec(3, 64, 7, 7), ops.ConvSpec(64, 3, 4, 4, L.WMAP_S2D, 32), ops.ConvSpec(40, 72, 3, 3)]
+    ws = [rnd(sp.co, sp.ci, sp.kh, sp.kw, seed=40 + i) for i, sp in enumerate(specs)]
+    wk = [torch.zeros(sp.packed_shape(False), dtype=dt, device="cuda") for sp in specs]
+    wkT = [torch.zeros(sp.packed_shape(True), dtype=dt, device="cuda") for sp in specs]
+    table = ops.wjob_table([(sp, w, a, b) for sp, w, a, b in zip(specs, ws, wk, wkT)], ws[0].device)
+    ops.wpack_multi(table, dt)
+    for sp, w, a, b in zip(specs, ws, wk, wkT):
+        ra, rb = torch.empty_like(a), torch.empty_like(b)
+        ops.wpack(sp, w, ra, False)
+        ops.wpack(sp, w, rb, True)
+        assert torch.equal(a, ra), f"forward layout {sp}"
+        assert torch.equal(b, rb), f"data-gradient layout {sp}"
+    # unpack: grad += unpack(dw); dw = 0
+    dws = [rnd(*sp.packed_shape(False), seed=60 + i) for i, sp in enumerate(specs)]
+    grads = [torch.ones_like(w) for w in ws]
+    refs = []
+    for sp, dw in zip(specs, dws):
+        g = torch.ones(sp.co, sp.ci, sp.kh, sp.kw, device="cuda")
+        ops.wunpack_grad(sp, dw, g, True)
+        refs.append(g)
+    ops.wunpack_multi(ops.wjob_table([(sp, g, dw, None) for sp, g, dw in zip(specs, grads, dws)], ws[0].device))
+    for sp, g, r, dw in zip(specs, grads, refs, dws):
+        assert torch.equal(g, r), f"unpack {sp}"
+        # every position that maps to a real weight was re-zeroed (padding positions are never read)
+        chk = torch.zeros_like(g)
+        ops.wunpack_grad(sp, dw, chk, False)
+        assert float(chk.abs().max()) == 0.0, f"accumulator not cleared {sp}"
+    # bias-style vector flush
+    src = [rnd(16, seed=80), rnd(8, seed=81)]
+    dst = [torch.ones(10, device="cuda"), torch.ones(3, device="cuda")]
+    exp = [dst[0] + src[0][:10], dst[1] + src[1][:3]]
+    ops.vecflush_multi(ops.vecjob_table([(src[0], dst[0], 10), (src[1], dst[1], 3)], src[0].device))
+    assert torch.equal(dst[0], exp[0]) and torch.equal(dst[1], exp[1])
+    assert float(src[0][:10].abs().max()) == 0.0 and float(src[0][10:].abs().min()) > 0.0
+
+
+# --------------------------------------------------------------------------------------------
 def test_losses(K):
     ops, L = K
     a, b = rnd(4, 3, 64, 64, seed=21), rnd(4, 3, 64, 64, seed=22)

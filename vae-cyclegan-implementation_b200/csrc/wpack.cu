@@ -73,6 +73,201 @@ __global__ void wunpack_kernel(const float* __restrict__ dwp, float* __restrict_
   g[idx] = accumulate ? g[idx] + v : v;
 }
 
+// ---- multi-tensor variants: ONE launch converts every filter of a network ------------------------------
+// A block owns a (CO_T output channels) x (32 input channels) x (all taps) tile of one filter and moves it through
+// shared memory, so that the OIHW side is accessed as contiguous runs of 32*taps floats and the packed side as
+// runs of 32 channels: both sides coalesced (the per-element kernels above read with a stride of kh*kw floats).
+struct WJob {
+  WpArgs a;
+  float* oihw;          // pack: fp32 master weight (read); unpack: gradient (written)
+  void* packed;         // forward layout (pack: dtype T; unpack: fp32 dw accumulator, re-zeroed after reading)
+  void* packed_t;       // pack only: data-gradient layout (may be null)
+  int t_kwc_pad;        // row length per tap row of packed_t
+  int accumulate;       // unpack: grad += instead of grad =
+  int co_t, tiles_ci, tile0, ntiles;
+};
+
+constexpr int kWTileFloats = 10240;   // 40 KB: 32 x 32 x 9(+1) fp32 for 3x3 filters
+
+__device__ __forceinline__ void map_tap(const WpArgs& p, int ci, int kh, int kw, int& ph, int& khp, int& kwp) {
+  khp = kh; kwp = kw;
+  if (p.wmap == VCG_WMAP_PLAIN) ph = ci;
+  else if (p.wmap == VCG_WMAP_UNSHUFFLE) { const int c0 = p.ci / 4; ph = (ci & 3) * c0 + (ci >> 2); }
+  else { khp = kh >> 1; kwp = kw >> 1; ph = ((kh & 1) * 2 + (kw & 1)) * (p.c_phys / 4) + ci; }
+}
+
+// the job record of this block, staged through shared memory (one global read per block, no per-use reloads)
+__device__ __forceinline__ WJob find_job(const WJob* __restrict__ jobs, int njobs, int tile) {
+  __shared__ WJob s_job;
+  if (threadIdx.x < 32) {
+    // 32 lanes test 32 jobs at a time: the last job whose first tile is <= tile
+    int found = 0;
+    for (int j0 = 0; j0 < njobs; j0 += 32) {
+      const int j = j0 + threadIdx.x;
+      const bool ok = j < njobs && jobs[j].tile0 <= tile;
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (m) found = j0 + 31 - __clz(m);
+    }
+    if (threadIdx.x == 0) s_job = jobs[found];
+  }
+  __syncthreads();
+  return s_job;
+}
+
+// per-tap offset tables (shared memory): packed offsets are separable into an output-channel term, a tap term and an
+// input-channel term, so the hot loops need no division:
+//   forward layout  : off = co * (pkh*kwc_pad)      + t_fwd[tap] + ph_ci(ci)
+//   data-grad layout: off = ph_ci(ci) * (pkh*t_kwc) + t_bwd[tap] + co
+__device__ __forceinline__ int ph_ci(const WpArgs& p, int ci) {
+  if (p.wmap == VCG_WMAP_UNSHUFFLE) { const int c0 = p.ci / 4; return (ci & 3) * c0 + (ci >> 2); }
+  return ci;
+}
+__device__ __forceinline__ void build_tap_tables(const WpArgs& p, int t_kwc, int* t_fwd, int* t_bwd) {
+  const int taps = p.kh * p.kw;
+  for (int tap = threadIdx.x; tap < taps; tap += blockDim.x) {
+    int ph, khp, kwp;
+    map_tap(p, 0, tap / p.kw, tap % p.kw, ph, khp, kwp);       // ph = tap-dependent part of the physical channel
+    if (p.wmap != VCG_WMAP_S2D) ph = 0;
+    t_fwd[tap] = khp * p.kwc_pad + kwp * p.c_phys + ph;
+    t_bwd[tap] = ph * p.pkh * t_kwc + (p.pkh - 1 - khp) * t_kwc + (p.pkw - 1 - kwp) * p.co_phys;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+wpack_multi_kernel(const WJob* __restrict__ jobs, int njobs) {
+  extern __shared__ float s_tile[];
+  __shared__ int t_fwd[64], t_bwd[64];
+  const WJob jb = find_job(jobs, njobs, blockIdx.x);
+  const WpArgs p = jb.a;
+  const int t = blockIdx.x - jb.tile0;
+  const int co0 = (t / jb.tiles_ci) * jb.co_t, ci0 = (t % jb.tiles_ci) * 32;
+  const int nco = min(jb.co_t, p.co - co0), nci = min(32, p.ci - ci0);
+  const int taps = p.kh * p.kw, ts = taps | 1;
+  build_tap_tables(p, jb.t_kwc_pad, t_fwd, t_bwd);
+  // phase 1: OIHW runs (nci*taps contiguous floats per output channel) -> s[co_l][ci_l][tap]; 4 loads in flight
+  const float* __restrict__ wsrc = jb.oihw;
+  const int run = nci * taps, n1 = nco * run;
+  for (int e0 = threadIdx.x; e0 < n1; e0 += 4 * 256) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * 256;
+      if (e < n1) {
+        const int col = e / run, k = e - col * run;
+        v[u] = wsrc[(static_cast<size_t>(co0 + col) * p.ci + ci0) * taps + k];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * 256;
+      if (e < n1) {
+        const int col = e / run, k = e - col * run;
+        const int cil = k / taps, tap = k - cil * taps;
+        s_tile[(col * 32 + cil) * ts + tap] = v[u];
+      }
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // phase 2a: forward layout: one (output channel, tap) row of 32 input channels per warp iteration
+  {
+    T* out = static_cast<T*>(jb.packed);
+    const size_t co_stride = static_cast<size_t>(p.pkh) * p.kwc_pad;
+    const int pc = lane < nci ? ph_ci(p, ci0 + lane) : 0;
+    int tap = warp % taps, col = warp / taps;           // rows r = warp, warp+8, ... ; r = col*taps + tap
+    for (; col < nco; ) {
+      if (lane < nci) Elem<T>::st(out + (co0 + col) * co_stride + t_fwd[tap] + pc, s_tile[(col * 32 + lane) * ts + tap]);
+      tap += 8;
+      while (tap >= taps) { tap -= taps; ++col; }
+    }
+  }
+  // phase 2b: data-gradient layout (rows = physical cin, taps flipped): one (input channel, tap) row of co_t
+  // output channels per warp iteration
+  if (jb.packed_t) {
+    T* outT = static_cast<T*>(jb.packed_t);
+    const size_t ci_stride = static_cast<size_t>(p.pkh) * jb.t_kwc_pad;
+    int tap = warp % taps, cil = warp / taps;
+    for (; cil < nci; ) {
+      if (lane < nco)
+        Elem<T>::st(outT + ph_ci(p, ci0 + cil) * ci_stride + t_bwd[tap] + co0 + lane, s_tile[(lane * 32 + cil) * ts + tap]);
+      tap += 8;
+      while (tap >= taps) { tap -= taps; ++cil; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+wunpack_multi_kernel(const WJob* __restrict__ jobs, int njobs) {
+  extern __shared__ float s_tile[];
+  __shared__ int t_fwd[64], t_bwd[64];
+  const WJob jb = find_job(jobs, njobs, blockIdx.x);
+  const WpArgs p = jb.a;
+  const int t = blockIdx.x - jb.tile0;
+  const int co0 = (t / jb.tiles_ci) * jb.co_t, ci0 = (t % jb.tiles_ci) * 32;
+  const int nco = min(jb.co_t, p.co - co0), nci = min(32, p.ci - ci0);
+  const int taps = p.kh * p.kw, ts = taps | 1;
+  build_tap_tables(p, 0, t_fwd, t_bwd);
+  __syncthreads();
+  // phase 1: packed fp32 accumulator rows (32 input channels of one (output channel, tap)) -> s[co_l][ci_l][tap];
+  // the accumulator is re-zeroed.  Four rows per warp iteration: the loads are issued before the stores.
+  {
+    float* __restrict__ dwp = static_cast<float*>(jb.packed);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t co_stride = static_cast<size_t>(p.pkh) * p.kwc_pad;
+    const int pc = lane < nci ? ph_ci(p, ci0 + lane) : 0;
+    const int nrows = nco * taps;
+    for (int r0 = warp; r0 < nrows; r0 += 32) {
+      float v[4];
+      float* ptr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + 8 * u;
+        ptr[u] = nullptr;
+        if (r < nrows && lane < nci) {
+          const int col = r / taps, tap = r - col * taps;
+          ptr[u] = dwp + (co0 + col) * co_stride + t_fwd[tap] + pc;
+          v[u] = *ptr[u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ptr[u]) {
+          const int r = r0 + 8 * u;
+          const int col = r / taps, tap = r - col * taps;
+          s_tile[(col * 32 + lane) * ts + tap] = v[u];
+          *ptr[u] = 0.f;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // phase 2: OIHW runs: the tile's rows are contiguous runs of nci*taps floats, CI*taps apart
+  float* __restrict__ g = jb.oihw;
+  const int run = nci * taps;
+  const int n2 = nco * run;
+  const bool acc = jb.accumulate != 0;
+  for (int e0 = threadIdx.x; e0 < n2; e0 += 4 * 256) {
+    float v[4];
+    size_t off[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * 256;
+      off[u] = static_cast<size_t>(-1);
+      if (e < n2) {
+        const int col = e / run, k = e - col * run;
+        off[u] = (static_cast<size_t>(co0 + col) * p.ci + ci0) * taps + k;
+        const int cil = k / taps, tap = k - cil * taps;
+        v[u] = s_tile[(col * 32 + cil) * ts + tap];
+        if (acc) v[u] += g[off[u]];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (off[u] != static_cast<size_t>(-1)) g[off[u]] = v[u];
+  }
+}
+
 WpArgs to_args(const vcg_wpack_desc* d) {
   WpArgs a;
   a.co = d->co; a.ci = d->ci; a.kh = d->kh; a.kw = d->kw; a.wmap = d->wmap; a.c_phys = d->c_phys;
@@ -107,5 +302,63 @@ extern "C" int vcg_wunpack_grad(const vcg_wpack_desc* d, const float* dw_packed,
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   wunpack_kernel<<<blocks, 256, 0, stream>>>(dw_packed, grad_oihw, to_args(d), accumulate, total);
   VCG_CHECK_LAUNCH("wunpack_kernel");
+  return VCG_OK;
+}
+
+namespace {
+struct VecJob { float* src; float* dst; int n, pad; };
+// dst[i] += src[i]; src[i] = 0  for every job (bias-gradient accumulators -> .grad), one block per job
+__global__ void vecflush_multi_kernel(const VecJob* __restrict__ jobs) {
+  const VecJob jb = jobs[blockIdx.x];
+  for (int i = threadIdx.x; i < jb.n; i += blockDim.x) { jb.dst[i] += jb.src[i]; jb.src[i] = 0.f; }
+}
+}  // namespace
+
+static_assert(sizeof(vcg_vecjob) == sizeof(VecJob), "vcg_vecjob layout mismatch");
+extern "C" int vcg_vecflush_multi(const vcg_vecjob* jobs_dev, int32_t njobs, void* stream_) {
+  if (njobs <= 0) return VCG_OK;
+  vecflush_multi_kernel<<<njobs, 128, 0, static_cast<cudaStream_t>(stream_)>>>(reinterpret_cast<const VecJob*>(jobs_dev));
+  VCG_CHECK_LAUNCH("vecflush_multi_kernel");
+  return VCG_OK;
+}
+
+// ---- multi-tensor entry points.  jobs: DEVICE array of njobs vcg_wjob records whose tile0 / ntiles fields were
+// filled by vcg_wjob_plan (host); total_tiles = sum of ntiles.
+extern "C" int vcg_wjob_plan(vcg_wjob* jobs_host, int32_t njobs, int32_t* total_tiles) {
+  int tile0 = 0;
+  for (int j = 0; j < njobs; ++j) {
+    vcg_wjob& jb = jobs_host[j];
+    const int taps = jb.kh * jb.kw;
+    VCG_REQUIRE(taps > 0 && 32 * (taps | 1) <= kWTileFloats, VCG_E_UNSUPPORTED, "wjob_plan: %d taps", taps);
+    int co_t = kWTileFloats / (32 * (taps | 1));
+    if (co_t > 32) co_t = 32;
+    jb.co_t = co_t;
+    jb.tiles_ci = (jb.ci + 31) / 32;
+    jb.tile0 = tile0;
+    jb.ntiles = ((jb.co + co_t - 1) / co_t) * jb.tiles_ci;
+    tile0 += jb.ntiles;
+  }
+  *total_tiles = tile0;
+  return VCG_OK;
+}
+
+static_assert(sizeof(vcg_wjob) == sizeof(WJob), "vcg_wjob / WJob layout mismatch");
+
+extern "C" int vcg_wpack_multi(int32_t dtype, const vcg_wjob* jobs_dev, int32_t njobs, int32_t total_tiles, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (njobs <= 0 || total_tiles <= 0) return VCG_OK;
+  const WJob* jobs = reinterpret_cast<const WJob*>(jobs_dev);
+  const size_t smem = kWTileFloats * sizeof(float);
+  if (dtype == VCG_F32) wpack_multi_kernel<float><<<total_tiles, 256, smem, stream>>>(jobs, njobs);
+  else wpack_multi_kernel<__nv_bfloat16><<<total_tiles, 256, smem, stream>>>(jobs, njobs);
+  VCG_CHECK_LAUNCH("wpack_multi_kernel");
+  return VCG_OK;
+}
+
+extern "C" int vcg_wunpack_multi(const vcg_wjob* jobs_dev, int32_t njobs, int32_t total_tiles, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (njobs <= 0 || total_tiles <= 0) return VCG_OK;
+  wunpack_multi_kernel<<<total_tiles, 256, kWTileFloats * sizeof(float), stream>>>(reinterpret_cast<const WJob*>(jobs_dev), njobs);
+  VCG_CHECK_LAUNCH("wunpack_multi_kernel");
   return VCG_OK;
 }

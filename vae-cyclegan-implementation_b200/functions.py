@@ -44,7 +44,9 @@ class PlanFunction(torch.autograd.Function):
         need = ctx.needs_input_grad[4:]
         if not _STATE.get("input_grads", True):      # discriminator step: stop at the network inputs
             need = tuple(False for _ in need)
-        gin = ctx.plan.run_backward(ctx.run, grads, need)
+        from .plan import queue_flush
+        gin = ctx.plan.run_backward(ctx.run, grads, need, defer_flush=True)
+        queue_flush()       # weight / bias gradient accumulators -> .grad once, after the whole backward pass
         return (None, None, None, None, *gin)
 
 

@@ -45,6 +45,16 @@ class XbwdDesc(C.Structure):
     _fields_ = _fields("dtype", "n", "h", "w", "c", "y_c", "norm", "act", "pre_act", "dy_halo", "dy_c", "nsrc")
 
 
+class WJob(C.Structure):
+    _fields_ = _fields("co", "ci", "kh", "kw", "wmap", "c_phys", "co_phys", "rows_pad", "pkh", "pkw", "kwc_pad",
+                       "transpose_flip") + [("oihw", C.c_void_p), ("packed", C.c_void_p), ("packed_t", C.c_void_p)] + \
+        _fields("t_kwc_pad", "accumulate", "co_t", "tiles_ci", "tile0", "ntiles")
+
+
+class VecJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n", i32), ("pad", i32)]
+
+
 class AdamChunk(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("numel", i32)]
 
@@ -61,6 +71,10 @@ _SIGS = {
     "vcg_conv_wgrad": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, C.c_void_p]),
     "vcg_wpack": (C.c_int, [C.POINTER(WpackDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "vcg_wunpack_grad": (C.c_int, [C.POINTER(WpackDesc), C.c_void_p, C.c_void_p, i32, C.c_void_p]),
+    "vcg_wjob_plan": (C.c_int, [C.POINTER(WJob), i32, C.POINTER(i32)]),
+    "vcg_wpack_multi": (C.c_int, [i32, C.c_void_p, i32, i32, C.c_void_p]),
+    "vcg_wunpack_multi": (C.c_int, [C.c_void_p, i32, i32, C.c_void_p]),
+    "vcg_vecflush_multi": (C.c_int, [C.c_void_p, i32, C.c_void_p]),
     "vcg_in_stats": (C.c_int, [i32, C.c_void_p, i32, i32, i32, i32, C.c_void_p, C.c_void_p]),
     "vcg_in_finalize": (C.c_int, [C.c_void_p, i32, i32, C.c_void_p, C.c_void_p]),
     "vcg_xform_fwd": (C.c_int, [C.POINTER(XformDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -153,6 +153,60 @@ def wpack(spec: ConvSpec, w_oihw, out, transpose_flip=False):
     return out
 
 
+def _to_device_bytes(carray, device):
+    import numpy as np
+    return torch.from_numpy(np.frombuffer(bytes(carray), dtype=np.uint8).copy()).to(device)
+
+
+def wjob_table(entries, device):
+    """entries: list of (spec, oihw fp32 tensor, packed fwd tensor, packed data-gradient tensor or None).
+    Returns (device byte tensor holding the vcg_wjob array, njobs, total_tiles) for vcg_wpack_multi /
+    vcg_wunpack_multi; build once and cache (the pointers must stay valid)."""
+    arr = (L.WJob * len(entries))()
+    for j, (spec, oihw, packed, packed_t) in enumerate(entries):
+        d = spec.wpack_desc(packed.dtype, False)
+        for f in ("co", "ci", "kh", "kw", "wmap", "c_phys", "co_phys", "rows_pad", "pkh", "pkw", "kwc_pad"):
+            setattr(arr[j], f, getattr(d, f))
+        assert oihw.dtype == torch.float32 and oihw.is_contiguous()
+        assert tuple(packed.shape) == spec.packed_shape(False)
+        arr[j].oihw, arr[j].packed = oihw.data_ptr(), packed.data_ptr()
+        if packed_t is not None:
+            assert tuple(packed_t.shape) == spec.packed_shape(True) and packed_t.dtype == packed.dtype
+            arr[j].packed_t, arr[j].t_kwc_pad = packed_t.data_ptr(), spec.d_kwc_pad
+        arr[j].accumulate = 1
+    total = C.c_int32(0)
+    L.check(L.load().vcg_wjob_plan(arr, len(entries), C.byref(total)), "vcg_wjob_plan")
+    return _to_device_bytes(arr, device), len(entries), int(total.value)
+
+
+@_profiled("wpack")
+def wpack_multi(table, dtype):
+    """OIHW fp32 masters -> both kernel layouts of every filter in the table, one launch"""
+    dev, n, tiles = table
+    L.check(L.load().vcg_wpack_multi(L.dtype_code(dtype), L.ptr(dev), n, tiles, L.stream_ptr()), "vcg_wpack_multi")
+
+
+@_profiled("wunpack_grad")
+def wunpack_multi(table):
+    """grad_oihw += unpack(dw); dw = 0 for every filter in the table, one launch"""
+    dev, n, tiles = table
+    L.check(L.load().vcg_wunpack_multi(L.ptr(dev), n, tiles, L.stream_ptr()), "vcg_wunpack_multi")
+
+
+def vecjob_table(entries, device):
+    """entries: list of (src fp32 tensor, dst fp32 tensor, n)"""
+    arr = (L.VecJob * len(entries))()
+    for j, (src, dst, n) in enumerate(entries):
+        arr[j].src, arr[j].dst, arr[j].n = src.data_ptr(), dst.data_ptr(), n
+    return _to_device_bytes(arr, device), len(entries)
+
+
+@_profiled("wunpack_grad")
+def vecflush_multi(table):
+    dev, n = table
+    L.check(L.load().vcg_vecflush_multi(L.ptr(dev), n, L.stream_ptr()), "vcg_vecflush_multi")
+
+
 @_profiled("wunpack_grad")
 def wunpack_grad(spec: ConvSpec, dw_packed, grad_oihw, accumulate=False):
     d = spec.wpack_desc(torch.float32, False)

@@ -75,6 +75,8 @@ class FusedAdam(torch.optim.Adam):
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        from . import plan
+        plan.flush_grads()          # no-op unless a backward was driven outside autograd
         if self.pre_step_hook is not None:
             self.pre_step_hook(self)
         for group in self.param_groups:

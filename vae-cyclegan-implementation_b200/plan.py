@@ -144,36 +144,127 @@ class PlanBuilder:
 
 
 # ----------------------------------------------------------------------------- parameter caches
+_TABLES = {}      # cached device-side job tables of the multi-tensor pack / unpack launches (keyed by pointers)
+_PENDING = []     # PackedConvs whose fp32 accumulators hold weight gradient not yet added to .grad
+_FLUSH_QUEUED = [False]
+
+
+def _cached_table(key, build):
+    t = _TABLES.get(key)
+    if t is None:
+        if len(_TABLES) > 256:
+            _TABLES.clear()
+        t = _TABLES[key] = build()
+    return t
+
+
 class PackedConv:
     """Kernel-layout copies of one conv's master weight, refreshed when the master changes
-    (tensor._version is bumped by the optimiser's in-place update and by load_state_dict)."""
+    (tensor._version is bumped by load_state_dict, _vcg_epoch by the fused optimiser), and the fp32
+    accumulators the weight-gradient GEMMs add into.  Accumulators are zero-initialised once; flush_grads()
+    adds them to .grad and re-zeroes them in the same launch, so no per-step clearing is needed."""
 
     def __init__(self, holder, spec):
         self.holder, self.spec = holder, spec
         self.key = None
         self.wk = self.wkT = self.dw = self.dbias = None
+        self.pending = self.pending_bias = False
+
+    def _key(self, dtype):
+        w = self.holder.weight
+        return (w._version, getattr(w, "_vcg_epoch", 0), w.data_ptr(), dtype, w.device)
+
+    def stale(self, dtype):
+        return self._key(dtype) != self.key
+
+    def buffers(self, dtype):
+        w = self.holder.weight
+        if self.wk is None or self.wk.dtype != dtype or self.wk.device != w.device:
+            # zero-filled: the padding rows / columns are never written by the multi-tensor pack
+            self.wk = torch.zeros(self.spec.packed_shape(False), dtype=dtype, device=w.device)
+            self.wkT = torch.zeros(self.spec.packed_shape(True), dtype=dtype, device=w.device)
+        return self.wk, self.wkT
 
     def refresh(self, dtype):
-        w = self.holder.weight
-        key = (w._version, getattr(w, "_vcg_epoch", 0), w.data_ptr(), dtype, w.device)
-        if key != self.key:
-            wc = w.detach()
-            if not wc.is_contiguous():
-                wc = wc.contiguous()
-            if self.wk is None or self.wk.dtype != dtype or self.wk.device != w.device:
-                self.wk = torch.empty(self.spec.packed_shape(False), dtype=dtype, device=w.device)
-                self.wkT = torch.empty(self.spec.packed_shape(True), dtype=dtype, device=w.device)
-            ops.wpack(self.spec, wc, self.wk, False)
-            ops.wpack(self.spec, wc, self.wkT, True)
-            self.key = key
+        if self.stale(dtype):
+            refresh_many([self], dtype)
         return self
 
     def grad_buffers(self):
         dev = self.holder.weight.device
         if self.dw is None or self.dw.device != dev:
-            self.dw = torch.empty(self.spec.packed_shape(False), dtype=torch.float32, device=dev)
-            self.dbias = torch.empty(ops.rup(self.spec.co, 8), dtype=torch.float32, device=dev)
+            self.dw = torch.zeros(self.spec.packed_shape(False), dtype=torch.float32, device=dev)
+            self.dbias = torch.zeros(ops.rup(self.spec.co, 8), dtype=torch.float32, device=dev)
         return self.dw, self.dbias
+
+    def mark_pending(self, bias):
+        if not self.pending:
+            self.pending = True
+            _PENDING.append(self)
+        self.pending_bias = self.pending_bias or bias
+
+
+def refresh_many(pcs, dtype):
+    """Re-pack every stale filter of `pcs` (both layouts) with ONE multi-tensor launch."""
+    stale, seen = [], set()
+    for pc in pcs:
+        if id(pc) not in seen and pc.stale(dtype):
+            seen.add(id(pc))
+            stale.append(pc)
+    if not stale:
+        return
+    entries, cacheable = [], True
+    for pc in stale:
+        w = pc.holder.weight.detach()
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w, cacheable = w.float().contiguous(), False
+        wk, wkT = pc.buffers(dtype)
+        entries.append((pc.spec, w, wk, wkT))
+    dev = entries[0][1].device
+    key = ("pack", dtype, tuple((e[1].data_ptr(), e[2].data_ptr(), e[3].data_ptr()) for e in entries))
+    table = _cached_table(key, lambda: ops.wjob_table(entries, dev)) if cacheable else ops.wjob_table(entries, dev)
+    ops.wpack_multi(table, dtype)
+    for pc in stale:
+        pc.key = pc._key(dtype)
+
+
+def flush_grads():
+    """Add every pending weight / bias gradient accumulator to its parameter's .grad (and re-zero the
+    accumulators): two multi-tensor launches for the whole model instead of one unpack per convolution."""
+    if not _PENDING:
+        return
+    pcs = list(_PENDING)
+    _PENDING.clear()
+    went, bent = [], []
+    for pc in pcs:
+        w = pc.holder.weight
+        if w.grad is None:
+            w.grad = torch.zeros_like(w, memory_format=torch.contiguous_format)
+        went.append((pc.spec, w.grad, pc.dw, None))
+        if pc.pending_bias:
+            b = pc.holder.bias
+            if b.grad is None:
+                b.grad = torch.zeros_like(b)
+            bent.append((pc.dbias, b.grad, pc.spec.co))
+        pc.pending = pc.pending_bias = False
+    dev = went[0][1].device
+    key = ("unpack", tuple((e[1].data_ptr(), e[2].data_ptr()) for e in went))
+    ops.wunpack_multi(_cached_table(key, lambda: ops.wjob_table(went, dev)))
+    if bent:
+        key = ("vec", tuple((e[0].data_ptr(), e[1].data_ptr()) for e in bent))
+        ops.vecflush_multi(_cached_table(key, lambda: ops.vecjob_table(bent, dev)))
+
+
+def queue_flush():
+    """Called from inside an autograd backward: flush once, when the whole backward pass has finished."""
+    if _FLUSH_QUEUED[0]:
+        return
+    _FLUSH_QUEUED[0] = True
+
+    def cb():
+        _FLUSH_QUEUED[0] = False
+        flush_grads()
+    torch.autograd.Variable._execution_engine.queue_callback(cb)
 
 
 def packed_for(holder, spec):
@@ -248,6 +339,16 @@ class Plan:
         outs = []
         node_out = {}
         out_nodes = {id(o[0]): o[1] for o in self.outputs}
+        convs = [nd for nd in self.nodes if isinstance(nd, ConvNode)]
+        refresh_many([packed_for(nd.holder, nd.spec) for nd in convs], dtype)      # one launch when weights changed
+        # InstanceNorm sum / sum-of-squares accumulators of all layers: one buffer, one clear
+        stat_off, total = {}, 0
+        if dtype == torch.bfloat16:
+            for nd in convs:
+                if nd.out_acts[0].norm:
+                    stat_off[nd] = total
+                    total += n * nd.spec.co * 2
+        stat_arena = ops.zero_(torch.empty(total, dtype=torch.float32, device=dev)) if total else None
         for node in self.nodes:
             if isinstance(node, ConvNode):
                 xp = self._materialize(run, node.inp, node.mode, node.pad, dtype)
@@ -265,7 +366,7 @@ class Plan:
                                 dtype=torch.float32 if (final_image or bottleneck) else dtype, device=dev)
                 bias = node.holder.bias.detach()
                 if a0.norm and dtype == torch.bfloat16:
-                    acc = ops.zero_(torch.empty(n * node.spec.co * 2, dtype=torch.float32, device=dev))
+                    acc = stat_arena[stat_off[node]:stat_off[node] + n * node.spec.co * 2]
                     ops.conv_fwd(node.spec, xp, pc.wk, bias, y, acc, node.pre_act)
                     run.MR[node] = ops.in_finalize(acc, n * node.spec.co, a0.h * a0.w, torch.empty_like(acc))
                 else:
@@ -321,11 +422,19 @@ class Plan:
         return ops.unpack_nchw(src, act.c_log, out)
 
     # ------------------------------------------------------------------ backward
-    def run_backward(self, run, grads, need_input_grad=(False,)):
+    def run_backward(self, run, grads, need_input_grad=(False,), defer_flush=False):
         """grads: one NCHW fp32 tensor (or None) per plan output, in output order.
-        Accumulates parameter gradients into .grad; returns input gradients (NCHW fp32 or None)."""
+        Accumulates parameter gradients into .grad (through the fp32 accumulators of the weight-gradient GEMMs,
+        flushed here unless defer_flush: the autograd wrapper flushes once at the end of the whole backward
+        pass); returns input gradients (NCHW fp32 or None)."""
         dtype = _STATE["dtype"]
         n = self.n
+        gs_off, gs_total = {}, 0
+        for nd in self.nodes:
+            if isinstance(nd, ConvNode) and nd.out_acts[0].norm:
+                gs_off[nd] = gs_total
+                gs_total += n * nd.spec.co * 2
+        gs_arena = None
         dense = {}        # act id -> list of dense NHWC grad tensors
         dxp = {}          # conv node -> padded-input gradient
         ext_mu, ext_lv, gscores = {}, {}, {}
@@ -420,27 +529,23 @@ class Plan:
                     y = None
                 pc = packed_for(holder, spec)
                 want_w = _wants_grad(holder.weight)
+                want_b = want_w and _wants_grad(holder.bias)
                 dw, dbias = pc.grad_buffers() if want_w else (None, None)
-                if want_w:
-                    ops.zero_(dbias)
+                if not want_b:
+                    dbias = None
                 if a0.norm:
                     mr = run.MR[node]
-                    gs = ops.zero_(torch.empty(n * spec.co * 2, dtype=torch.float32, device=dev))
+                    if gs_arena is None:      # per-(n,c) reduction buffers of all normalised layers: one clear
+                        gs_arena = ops.zero_(torch.empty(gs_total, dtype=torch.float32, device=dev))
+                    gs = gs_arena[gs_off[node]:gs_off[node] + n * spec.co * 2]
                     ops.xform_bwd_gather(srcs, y, n, a0.h, a0.w, spec.out_c, dy, halo, mr, a0.act, node.pre_act, gs, None)
                     ops.xform_bwd_norm(y, n, a0.h, a0.w, spec.out_c, dy, halo, mr, gs, node.pre_act, dbias)
                 else:
                     ops.xform_bwd_gather(srcs, y, n, a0.h, a0.w, spec.out_c, dy, halo, None, a0.act, node.pre_act, None, dbias)
                 xp = run.xp_of_node[node]
                 if want_w:
-                    ops.zero_(dw)
-                    ops.conv_wgrad(spec, xp, dy, dw)
-                    _accumulate_grad(holder.weight, lambda g, acc: ops.wunpack_grad(spec, dw, g, acc))
-                    if _wants_grad(holder.bias):
-                        db = dbias[:spec.co]
-                        if holder.bias.grad is None:
-                            holder.bias.grad = db.clone()
-                        else:
-                            holder.bias.grad.add_(db)
+                    ops.conv_wgrad(spec, xp, dy, dw)       # accumulates; added to .grad by flush_grads()
+                    pc.mark_pending(want_b)
                 if needs_dx(node.inp):
                     pc.refresh(dtype)
                     g = torch.empty_like(xp)
@@ -449,6 +554,8 @@ class Plan:
                     # gather of this gradient (it can feed two activations through a residual) reads one position
                     ops.fold_halo_(g, node.mode, node.pad, node.inp.h, node.inp.w, node.inp.c)
                     dxp[node] = g
+        if not defer_flush:
+            flush_grads()
         res = []
         for a, need in zip(self.inputs, need_input_grad):
             srcs = sources(a) if need else []
