@@ -147,6 +147,8 @@ typedef struct vcg_xform_desc {
   int32_t pad;               /* reflect halo width (destination domain; PAD_S2D: source domain) */
   int32_t dst_c;             /* destination physical channel pitch (extra channels zero-filled) */
   int32_t res_hp, res_wp, res_c, res_off;  /* residual: [n,res_hp,res_wp,res_c] read at (+off,+off) */
+  int32_t stats_hw;          /* >0: mean_rstd holds the RAW {sum, sum of squares} pairs of vcg_conv_fwd's statistics
+                                output over stats_hw pixels; mean / rstd (eps 1e-5, biased variance) are derived on load */
 } vcg_xform_desc;
 VCG_API int vcg_xform_fwd(const vcg_xform_desc* d, const void* src, const float* mean_rstd,
                   const void* residual, void* dst, void* stream);
@@ -168,6 +170,8 @@ typedef struct vcg_xbwd_desc {
   int32_t pre_act;           /* activation fused in the conv epilogue (before the norm) */
   int32_t dy_halo, dy_c;     /* destination geometry */
   int32_t nsrc;              /* 1..3 */
+  int32_t stats_hw;          /* as in vcg_xform_desc */
+  int32_t clear_halo;        /* gather only: also zero the halo ring of dy (saves a separate vcg_zero_halo launch) */
 } vcg_xbwd_desc;
 VCG_API int vcg_xform_bwd_gather(const vcg_xbwd_desc* d, const vcg_gsrc* srcs, const void* y,
                          const float* mean_rstd, void* dy, float* gsums /*[n,c,2]*/,

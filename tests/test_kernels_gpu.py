@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from util import assert_close, nchw, ref_unshuffle_phys, ref_xform, rel_l2
+from util import assert_close, nchw, nhwc, ref_unshuffle_phys, ref_xform, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -73,17 +73,21 @@ def test_xform_fwd_bwd(K, prec, case, folded):
     # ours
     src = torch.empty(n, h, w, c, dtype=dt, device="cuda")
     ops.pack_nchw(x, src)
-    mr = None
+    mr, shw = None, 0
     if norm:
         mr = torch.zeros(n * c * 6, dtype=torch.float32, device="cuda")
         ops.in_stats(src, c, mr)
+        if folded:      # production bf16 path: RAW {sum, sum of squares} pairs, mean / rstd derived on load (stats_hw)
+            xs = nhwc(x).reshape(n, h * w, c).double()
+            mr = torch.stack([xs.sum(1), (xs * xs).sum(1)], dim=-1).float().reshape(-1).contiguous()
+            shw = h * w
     resbuf = None
     if res:
         resbuf = torch.empty(n, h + 2, w + 2, c, dtype=dt, device="cuda")
         ops.pack_nchw(r, resbuf, halo=1)
     dshape = ops.xform_dst_shape(n, h, w, c, mode, pad)
     dst = torch.full(dshape, float("nan"), dtype=dt, device="cuda")
-    ops.xform_fwd(src, c, dst, mode, pad, mr, act, resbuf, 1 if res else 0)
+    ops.xform_fwd(src, c, dst, mode, pad, mr, act, resbuf, 1 if res else 0, stats_hw=shw)
     got = nchw(dst.float())[:, :ref.shape[1]]
     assert_close(got, ref.detach(), 1e-5 if prec == "fp32" else 6e-3, f"xform_fwd {case}", "nchw")
     # backward: gradient of sum(ref * G) w.r.t. x
@@ -91,13 +95,15 @@ def test_xform_fwd_bwd(K, prec, case, folded):
     (ref * G.double()).sum().backward()
     dxp = torch.zeros(dshape, dtype=dt, device="cuda")
     ops.pack_nchw(G, dxp)   # G is already in the destination domain
-    dy = torch.zeros(n, h + 2, w + 2, c, dtype=dt, device="cuda")
+    # folded variant: the gather clears the halo ring itself (clear_halo), so start from NaN
+    dy = torch.full((n, h + 2, w + 2, c), float("nan") if folded else 0.0, dtype=dt, device="cuda")
     gs = torch.zeros(n * c * 2, dtype=torch.float32, device="cuda") if norm else None
     if folded:      # adjoint of the reflect pad applied once, in place; the gather then takes its fast path
         ops.fold_halo_(dxp, mode, pad, h, w, c)
-    ops.xform_bwd_gather([(dxp, mode, pad, folded)], src, n, h, w, c, dy, 1, mr, act, 0, gs, None)
+    ops.xform_bwd_gather([(dxp, mode, pad, folded)], src, n, h, w, c, dy, 1, mr, act, 0, gs, None, stats_hw=shw,
+                         clear_halo=folded)
     if norm:
-        ops.xform_bwd_norm(src, n, h, w, c, dy, 1, mr, gs)
+        ops.xform_bwd_norm(src, n, h, w, c, dy, 1, mr, gs, stats_hw=shw)
     got_dx = nchw(dy[:, 1:-1, 1:-1].float())
     assert_close(got_dx, xr.grad, 2e-5 if prec == "fp32" else 1.5e-2, f"xform_bwd {case}", "nchw")
     assert float(dy[:, 0].abs().max()) == 0.0 and float(dy[:, :, -1].abs().max()) == 0.0, "halo must stay zero"

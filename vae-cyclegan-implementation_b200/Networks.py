@@ -308,9 +308,17 @@ class _Composite(_PlanModule):
     def enable_debug_mode(self, enabled=True):
         self.debug_mode = enabled
 
+    def _finish_steps(self):
+        """complete optimiser steps whose gradient exchange was left running (data-parallel overlap, dist.py)"""
+        for n in ("optimizer", "optimizer_G", "optimizer_D"):
+            o = getattr(self, n, None)
+            if o is not None and hasattr(o, "finish"):
+                o.finish()
+
     def _items(self, named):
         """dict of 0-d tensors -> dict of python floats with ONE device synchronisation (the reference
         pays one .item() sync per metric, Networks.py:2054-2076); averaged over ranks when data-parallel."""
+        self._finish_steps()
         keys = list(named)
         vals = torch.stack([named[k].detach().float().reshape(()) for k in keys])
         sync = getattr(self, "_vcg_sync", None)

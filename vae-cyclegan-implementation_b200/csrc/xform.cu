@@ -77,7 +77,7 @@ __global__ void in_finalize_f_kernel(const float* __restrict__ acc, int nc, int 
 // ------------------------------------------------------------------ forward transform
 struct XfArgs {
   int n, h, w, c, src_c, norm, act, mode, pad, dst_c, hd, wd, cd;  // cd = logical dst channels
-  int res_hp, res_wp, res_c, res_off;
+  int res_hp, res_wp, res_c, res_off, stats_hw;
 };
 
 // raw 8-element vectors: loads are issued into packed registers and unpacked only when consumed, so several
@@ -101,13 +101,46 @@ __device__ __forceinline__ void unpack(const Raw8<float>& v, float (&f)[8]) {
 constexpr int kXfRows = 4;   // rows per unrolled iteration: 4 independent 16-byte loads in flight per thread
 
 // per-channel statistics of the pending InstanceNorm for 8 consecutive channels: sc = rstd, sf = mean
-// (applied as (v - mean) * rstd, the reference's operation order, in both precisions)
-__device__ __forceinline__ void load_scale_shift(const float* __restrict__ m, float (&sc)[8], float (&sf)[8]) {
+// (applied as (v - mean) * rstd, the reference's operation order, in both precisions).
+// stats_hw > 0: the buffer holds the raw {sum, sum of squares} pairs accumulated by the convolution epilogue and
+// mean / rstd are derived here (same arithmetic as in_finalize_f_kernel), which saves one launch per layer.
+__device__ __forceinline__ void finalize_pair(float& a, float& b, int stats_hw) {
+  if (stats_hw > 0) {
+    const float inv = 1.f / stats_hw;
+    const float mean = a * inv;
+    float var = b * inv - mean * mean;
+    if (var < 0.f) var = 0.f;
+    a = mean;
+    b = rsqrtf(var + 1e-5f);
+  }
+}
+__device__ __forceinline__ void load_scale_shift(const float* __restrict__ m, float (&sc)[8], float (&sf)[8], int stats_hw) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float4 t = *reinterpret_cast<const float4*>(m + 4 * q);   // {mean, rstd, mean, rstd}
+    float4 t = *reinterpret_cast<const float4*>(m + 4 * q);   // {mean, rstd, mean, rstd} (or raw sums)
+    finalize_pair(t.x, t.y, stats_hw);
+    finalize_pair(t.z, t.w, stats_hw);
     sc[2 * q] = t.y; sf[2 * q] = t.x;
     sc[2 * q + 1] = t.w; sf[2 * q + 1] = t.z;
+  }
+}
+
+// zero this block's share of the halo ring of an NHWC buffer [n, h+2*halo, w+2*halo, c_pitch] (8-channel group ch)
+template <typename T>
+__device__ __forceinline__ void clear_halo_share(T* __restrict__ buf, int n, int h, int w, int halo, int c_pitch, int ch,
+                                                 int first, int step) {
+  const int hp = h + 2 * halo, wp = w + 2 * halo;
+  const int ring = hp * wp - h * w, top = halo * wp;
+  float z[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) z[j] = 0.f;
+  for (int r = first; r < ring; r += step) {
+    int a, b;
+    if (r < top) { a = r / wp; b = r - a * wp; }
+    else if (r < 2 * top) { const int q = r - top; a = halo + h + q / wp; b = q % wp; }
+    else { const int q = r - 2 * top; const int row = q / (2 * halo), k = q - row * 2 * halo;
+           a = halo + row; b = k < halo ? k : w + k; }
+    st8<T>(buf + ((static_cast<size_t>(n) * hp + a) * wp + b) * c_pitch + ch, z);
   }
 }
 
@@ -164,7 +197,7 @@ xform_fwd_kernel(const T* __restrict__ src, const float* __restrict__ mr, const 
     return reflect_idx(2 * a + (sub >> 1) - p.pad, p.h);
   };
   float sc[8], sf[8];
-  if (p.norm) load_scale_shift(mr + (static_cast<size_t>(n) * p.c + sc0) * 2, sc, sf);
+  if (p.norm) load_scale_shift(mr + (static_cast<size_t>(n) * p.c + sc0) * 2, sc, sf, p.stats_hw);
   const size_t srow = static_cast<size_t>(p.w) * p.src_c;
   const T* sbase = src + (static_cast<size_t>(n) * p.h * p.w + sw) * p.src_c + sc0;
   const size_t rrow = static_cast<size_t>(p.res_wp) * p.res_c;
@@ -221,7 +254,7 @@ xform_fwd_shuffle_kernel(const T* __restrict__ src, const float* __restrict__ mr
   const int r0 = blockIdx.y * rows_per_block, r1 = min(p.h, r0 + rows_per_block);
   const int H2 = 2 * p.h, W2 = 2 * p.w;
   float sc[8], sf[8];
-  if (p.norm) load_scale_shift(mr + (static_cast<size_t>(n) * p.c + sc0) * 2, sc, sf);
+  if (p.norm) load_scale_shift(mr + (static_cast<size_t>(n) * p.c + sc0) * 2, sc, sf, p.stats_hw);
   int cols[2][3];
 #pragma unroll
   for (int jj = 0; jj < 2; ++jj)
@@ -284,7 +317,7 @@ xform_fwd_shuffle_kernel(const T* __restrict__ src, const float* __restrict__ mr
 // ------------------------------------------------------------------ backward transform
 struct GSrc { const void* dxp; int mode, pad, c_pitch, folded; };
 struct XbArgs {
-  int n, h, w, c, y_c, norm, act, pre_act, dy_halo, dy_c, nsrc;
+  int n, h, w, c, y_c, norm, act, pre_act, dy_halo, dy_c, nsrc, stats_hw, clear_halo;
   GSrc s[3];
 };
 
@@ -386,7 +419,7 @@ xform_bwd_generic_kernel(const __grid_constant__ XbArgs p, const T* __restrict__
     if (p.norm) {
       const float* m = mr + (static_cast<size_t>(n) * p.c + ch) * 2;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { mean[j] = m[2 * j]; rstd[j] = m[2 * j + 1]; }
+      for (int j = 0; j < 8; ++j) { mean[j] = m[2 * j]; rstd[j] = m[2 * j + 1]; finalize_pair(mean[j], rstd[j], p.stats_hw); }
       if (PHASE2) {
         const float* gs = gsums_in + (static_cast<size_t>(n) * p.c + ch) * 2;
         const float inv = 1.f / hw;
@@ -394,6 +427,7 @@ xform_bwd_generic_kernel(const __grid_constant__ XbArgs p, const T* __restrict__
         for (int j = 0; j < 8; ++j) { m1[j] = gs[2 * j] * inv; m2[j] = gs[2 * j + 1] * inv; }
       }
     }
+    if (!PHASE2 && p.clear_halo && p.dy_halo > 0) clear_halo_share<T>(dy, n, p.h, p.w, p.dy_halo, p.dy_c, ch, blockIdx.x * lanes + pl, gridDim.x * lanes);
     const bool need_y = p.norm || p.act || p.pre_act;
     auto dy_ptr = [&](int pp) {
       const int h = pp / p.w, w = pp - h * p.w;
@@ -487,10 +521,6 @@ xform_bwd_generic_kernel(const __grid_constant__ XbArgs p, const T* __restrict__
 //  (c) the per-(n,c) sums are reduced with warp shuffles and one shared-memory slab row per warp.
 constexpr int kXbUmax = 4;
 
-__device__ __forceinline__ bool has_mirror(int i, int L, int pad) {
-  return (i >= 1 && i <= pad) || (i >= L - 1 - pad && i <= L - 2);
-}
-
 __device__ __forceinline__ void ldraw_pairs(const __nv_bfloat16* p0, const __nv_bfloat16* p1, const __nv_bfloat16* p2,
                                             const __nv_bfloat16* p3, Raw8<__nv_bfloat16>& v) {
   v.r.x = *reinterpret_cast<const uint32_t*>(p0); v.r.y = *reinterpret_cast<const uint32_t*>(p1);
@@ -512,7 +542,7 @@ struct FSrc {
   int hoff, woff, sh, msk, rs, cs, ph, pw, pitch, shuffle;
 };
 struct XgArgs {
-  int n, h, w, c, y_c, norm, act, pre_act, dy_halo, dy_c, nsrc;
+  int n, h, w, c, y_c, norm, act, pre_act, dy_halo, dy_c, nsrc, stats_hw, clear_halo;
   FSrc s[3];
 };
 
@@ -683,7 +713,8 @@ xform_bwd_gather_kernel(const __grid_constant__ XgArgs p, const T* __restrict__ 
 #pragma unroll
   for (int j = 0; j < 16; ++j) s[j] = 0.f;
   float sc[8], sf[8];
-  if (p.norm) load_scale_shift(mr + (static_cast<size_t>(n) * p.c + ch) * 2, sc, sf);
+  if (p.norm) load_scale_shift(mr + (static_cast<size_t>(n) * p.c + ch) * 2, sc, sf, p.stats_hw);
+  if (p.clear_halo && p.dy_halo > 0) clear_halo_share<T>(dy, n, p.h, p.w, p.dy_halo, p.dy_c, ch, blockIdx.x * lanes + pl, gridDim.x * lanes);
   const bool need_y = p.norm || p.act || p.pre_act;
   for (int pp = p0 + pl; pp < p1; pp += kXbU * lanes) {
     int hh[kXbU], ww[kXbU];
@@ -787,7 +818,7 @@ xform_bwd_norm_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y,
   const int wpd = p.w + 2 * p.dy_halo, hpd = p.h + 2 * p.dy_halo;
   float mean[8], rstd[8], m1[8], m2[8], s[8];
   {
-    load_scale_shift(mr + (static_cast<size_t>(n) * p.c + ch) * 2, rstd, mean);
+    load_scale_shift(mr + (static_cast<size_t>(n) * p.c + ch) * 2, rstd, mean, p.stats_hw);
     const float* gs = gsums_in + (static_cast<size_t>(n) * p.c + ch) * 2;
     const float inv = 1.f / hw;
 #pragma unroll
@@ -949,7 +980,7 @@ extern "C" int vcg_xform_fwd(const vcg_xform_desc* d, const void* src, const flo
   XfArgs a{};
   a.n = d->n; a.h = d->h; a.w = d->w; a.c = d->c; a.src_c = d->src_c; a.norm = d->norm; a.act = d->act;
   a.mode = d->mode; a.pad = d->pad; a.dst_c = d->dst_c;
-  a.res_hp = d->res_hp; a.res_wp = d->res_wp; a.res_c = d->res_c; a.res_off = d->res_off;
+  a.res_hp = d->res_hp; a.res_wp = d->res_wp; a.res_c = d->res_c; a.res_off = d->res_off; a.stats_hw = d->stats_hw;
   switch (d->mode) {
     case VCG_MODE_PLAIN: a.hd = d->h + 2 * d->pad; a.wd = d->w + 2 * d->pad; a.cd = d->c; break;
     case VCG_MODE_SHUFFLE:
@@ -999,6 +1030,7 @@ static int fill_xb(const vcg_xbwd_desc* d, const vcg_gsrc* srcs, XbArgs& a) {
   VCG_REQUIRE(d->nsrc >= 0 && d->nsrc <= 3, VCG_E_INVALID, "xform_bwd: nsrc=%d", d->nsrc);
   a.n = d->n; a.h = d->h; a.w = d->w; a.c = d->c; a.y_c = d->y_c; a.norm = d->norm; a.act = d->act;
   a.pre_act = d->pre_act; a.dy_halo = d->dy_halo; a.dy_c = d->dy_c; a.nsrc = d->nsrc;
+  a.stats_hw = d->stats_hw; a.clear_halo = d->clear_halo;
   for (int k = 0; k < d->nsrc && srcs; ++k) {
     a.s[k].dxp = srcs[k].dxp; a.s[k].mode = srcs[k].mode; a.s[k].pad = srcs[k].pad; a.s[k].c_pitch = srcs[k].c_pitch;
     a.s[k].folded = srcs[k].folded;
@@ -1022,6 +1054,7 @@ extern "C" int vcg_xform_bwd_gather(const vcg_xbwd_desc* d, const vcg_gsrc* srcs
     XgArgs g{};
     g.n = d->n; g.h = d->h; g.w = d->w; g.c = d->c; g.y_c = d->y_c; g.norm = d->norm; g.act = d->act;
     g.pre_act = d->pre_act; g.dy_halo = d->dy_halo; g.dy_c = d->dy_c; g.nsrc = d->nsrc;
+    g.stats_hw = d->stats_hw; g.clear_halo = d->clear_halo;
     const size_t es = d->dtype == VCG_F32 ? 4 : 2;
     for (int k = 0; k < d->nsrc; ++k) {
       FSrc& f = g.s[k];
@@ -1061,17 +1094,13 @@ extern "C" int vcg_xform_bwd_gather(const vcg_xbwd_desc* d, const vcg_gsrc* srcs
     }
     const int ppb = pix_chunk_fast(hw, d->n, zc, cg_total);
     dim3 grid((hw + ppb - 1) / ppb, d->n, zc);
-    static const int variant = getenv("VCG_XB_VARIANT") ? atoi(getenv("VCG_XB_VARIANT")) : 0;   // tuning experiment
-#define VCG_XB_LAUNCH(T, U, MINB)                                                                              \
-  xform_bwd_gather_kernel<T, U, MINB><<<grid, 256, 0, stream>>>(g, static_cast<const T*>(y), mean_rstd,       \
-                                                                static_cast<T*>(dy), gsums, dbias, ppb)
-    if (d->dtype == VCG_F32) VCG_XB_LAUNCH(float, 2, 2);
-    else if (variant == 1) VCG_XB_LAUNCH(__nv_bfloat16, 2, 3);
-    else if (variant == 2) VCG_XB_LAUNCH(__nv_bfloat16, 2, 4);
-    else if (variant == 3) VCG_XB_LAUNCH(__nv_bfloat16, 1, 4);
-    else if (variant == 4) VCG_XB_LAUNCH(__nv_bfloat16, 4, 1);
-    else VCG_XB_LAUNCH(__nv_bfloat16, 4, 2);
-#undef VCG_XB_LAUNCH
+    // 4 pixels per thread per iteration at 2 blocks/SM measured best on B200 (4.2 TB/s; 2 px x 3 blocks: 3.7)
+    if (d->dtype == VCG_F32)
+      xform_bwd_gather_kernel<float, 2, 2><<<grid, 256, 0, stream>>>(g, static_cast<const float*>(y), mean_rstd,
+                                                                     static_cast<float*>(dy), gsums, dbias, ppb);
+    else
+      xform_bwd_gather_kernel<__nv_bfloat16, 4, 2><<<grid, 256, 0, stream>>>(g, static_cast<const __nv_bfloat16*>(y), mean_rstd,
+                                                                             static_cast<__nv_bfloat16*>(dy), gsums, dbias, ppb);
     VCG_CHECK_LAUNCH("xform_bwd_gather_kernel");
     return VCG_OK;
   }

@@ -34,7 +34,7 @@ class WpackDesc(C.Structure):
 
 class XformDesc(C.Structure):
     _fields_ = _fields("dtype", "n", "h", "w", "c", "src_c", "norm", "act", "mode", "pad", "dst_c",
-                       "res_hp", "res_wp", "res_c", "res_off")
+                       "res_hp", "res_wp", "res_c", "res_off", "stats_hw")
 
 
 class GSrc(C.Structure):
@@ -42,7 +42,7 @@ class GSrc(C.Structure):
 
 
 class XbwdDesc(C.Structure):
-    _fields_ = _fields("dtype", "n", "h", "w", "c", "y_c", "norm", "act", "pre_act", "dy_halo", "dy_c", "nsrc")
+    _fields_ = _fields("dtype", "n", "h", "w", "c", "y_c", "norm", "act", "pre_act", "dy_halo", "dy_c", "nsrc", "stats_hw", "clear_halo")
 
 
 class WJob(C.Structure):

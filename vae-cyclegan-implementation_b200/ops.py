@@ -298,7 +298,7 @@ def xform_dst_shape(n, h, w, c, mode, pad, dst_c=None):
     return (n, hd, wd, dst_c or rup(cd, 8))
 
 
-def xform_fwd(src, c, dst, mode, pad, mean_rstd=None, act=L.ACT_NONE, residual=None, res_off=0):
+def xform_fwd(src, c, dst, mode, pad, mean_rstd=None, act=L.ACT_NONE, residual=None, res_off=0, stats_hw=0):
     n, h, w, src_c = src.shape
     tok = _rec("xform_fwd", float(src[..., :c].numel() * src.element_size() + dst.numel() * dst.element_size()),
                f"c{c} {h}x{w} mode{mode} pad{pad}{' norm' if mean_rstd is not None else ''}{' res' if residual is not None else ''}")
@@ -306,7 +306,7 @@ def xform_fwd(src, c, dst, mode, pad, mean_rstd=None, act=L.ACT_NONE, residual=N
                     norm=1 if mean_rstd is not None else 0, act=act, mode=mode, pad=pad, dst_c=dst.shape[-1],
                     res_hp=residual.shape[1] if residual is not None else 0,
                     res_wp=residual.shape[2] if residual is not None else 0,
-                    res_c=residual.shape[3] if residual is not None else 0, res_off=res_off)
+                    res_c=residual.shape[3] if residual is not None else 0, res_off=res_off, stats_hw=stats_hw)
     assert tuple(dst.shape) == xform_dst_shape(n, h, w, c, mode, pad, dst.shape[-1]), (dst.shape, src.shape, mode, pad)
     L.check(L.load().vcg_xform_fwd(C.byref(d), L.ptr(src), L.ptr(mean_rstd), L.ptr(residual), L.ptr(dst), L.stream_ptr()),
             "vcg_xform_fwd")
@@ -314,13 +314,14 @@ def xform_fwd(src, c, dst, mode, pad, mean_rstd=None, act=L.ACT_NONE, residual=N
     return dst
 
 
-def _xb_desc(y_like_dtype, n, h, w, c, y_c, norm, act, pre_act, dy, dy_halo, nsrc):
+def _xb_desc(y_like_dtype, n, h, w, c, y_c, norm, act, pre_act, dy, dy_halo, nsrc, stats_hw=0, clear_halo=0):
     return L.XbwdDesc(dtype=L.dtype_code(y_like_dtype), n=n, h=h, w=w, c=c, y_c=y_c, norm=1 if norm else 0, act=act,
-                      pre_act=pre_act, dy_halo=dy_halo, dy_c=dy.shape[-1], nsrc=nsrc)
+                      pre_act=pre_act, dy_halo=dy_halo, dy_c=dy.shape[-1], nsrc=nsrc, stats_hw=stats_hw,
+                      clear_halo=1 if clear_halo else 0)
 
 
 def xform_bwd_gather(srcs, y, n, h, w, c, dy, dy_halo, mean_rstd=None, act=L.ACT_NONE, pre_act=L.ACT_NONE,
-                     gsums=None, dbias=None):
+                     gsums=None, dbias=None, stats_hw=0, clear_halo=False):
     """srcs: list of (dxp tensor, mode, pad[, folded]).  Writes g into the interior of dy (+ sums for phase 2).
     folded=True: fold_halo_ already added the reflect halo of dxp into its interior (fast kernel)."""
     tok = _rec("xform_bwd_gather", float(sum(s[0].numel() * s[0].element_size() for s in srcs) + 2 * n * h * w * c * dy.element_size()),
@@ -332,7 +333,8 @@ def xform_bwd_gather(srcs, y, n, h, w, c, dy, dy_halo, mean_rstd=None, act=L.ACT
         arr[i].mode, arr[i].pad, arr[i].c_pitch = mode, pad, t.shape[-1]
         arr[i].folded = 1 if (len(src) > 3 and src[3]) else 0
     norm = mean_rstd is not None
-    d = _xb_desc(dy.dtype, n, h, w, c, y.shape[-1] if y is not None else 8, norm, act, pre_act, dy, dy_halo, len(srcs))
+    d = _xb_desc(dy.dtype, n, h, w, c, y.shape[-1] if y is not None else 8, norm, act, pre_act, dy, dy_halo, len(srcs),
+                 stats_hw, clear_halo)
     L.check(L.load().vcg_xform_bwd_gather(C.byref(d), arr, L.ptr(y), L.ptr(mean_rstd), L.ptr(dy), L.ptr(gsums),
                                           L.ptr(dbias), L.stream_ptr()), "vcg_xform_bwd_gather")
     _rec_end(tok)
@@ -348,9 +350,9 @@ def fold_halo_(dxp, mode, pad, h, w, c):
     return dxp
 
 
-def xform_bwd_norm(y, n, h, w, c, dy, dy_halo, mean_rstd, gsums, pre_act=L.ACT_NONE, dbias=None):
+def xform_bwd_norm(y, n, h, w, c, dy, dy_halo, mean_rstd, gsums, pre_act=L.ACT_NONE, dbias=None, stats_hw=0):
     tok = _rec("xform_bwd_norm", float(3 * n * h * w * c * dy.element_size()), f"c{c} {h}x{w}")
-    d = _xb_desc(dy.dtype, n, h, w, c, y.shape[-1], True, L.ACT_NONE, pre_act, dy, dy_halo, 0)
+    d = _xb_desc(dy.dtype, n, h, w, c, y.shape[-1], True, L.ACT_NONE, pre_act, dy, dy_halo, 0, stats_hw)
     L.check(L.load().vcg_xform_bwd_norm(C.byref(d), L.ptr(y), L.ptr(mean_rstd), L.ptr(gsums), L.ptr(dy), L.ptr(dbias),
                                         L.stream_ptr()), "vcg_xform_bwd_norm")
     _rec_end(tok)

@@ -19,6 +19,10 @@ CHUNK = 65536
 
 
 class FusedAdam(torch.optim.Adam):
+    def state_dict(self):
+        self.finish()
+        return super().state_dict()
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, flat_grads=True):
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, foreach=False)
         self._flat_grads = flat_grads
@@ -29,7 +33,11 @@ class FusedAdam(torch.optim.Adam):
         self._dev_step = 0
         self._last = None
         self.grad_scale = 1.0       # data-parallel averaging folded into the update (dist.py sets 1/world)
-        self.pre_step_hook = None   # dist.py: all-reduce of the flat gradient buffer
+        self.pre_step_hook = None   # dist.py: starts the all-reduce of the flat gradient buffer (side stream)
+        self.pre_update_hook = None  # dist.py: joins the all-reduce right before the Adam kernel
+        self.defer = False          # dist.py: step() only starts the all-reduce; finish() joins it and updates, so
+                                    # that the exchange overlaps whatever the caller runs in between
+        self._deferred = False
 
     # ---- flat gradient buffer -------------------------------------------------------------
     def _params(self):
@@ -48,6 +56,7 @@ class FusedAdam(torch.optim.Adam):
         return self._flat
 
     def zero_grad(self, set_to_none=True):
+        self.finish()
         if not self._flat_grads or not self._params() or not self._params()[0].is_cuda:
             return super().zero_grad(set_to_none)
         flat = self.flat_grad()
@@ -77,8 +86,25 @@ class FusedAdam(torch.optim.Adam):
         loss = closure() if closure is not None else None
         from . import plan
         plan.flush_grads()          # no-op unless a backward was driven outside autograd
+        self.finish()               # a previous deferred step of this optimiser
         if self.pre_step_hook is not None:
             self.pre_step_hook(self)
+        if self.defer:
+            self._deferred = True
+            return loss
+        self._update()
+        return loss
+
+    @torch.no_grad()
+    def finish(self):
+        """Complete a deferred step (join the gradient exchange, run the Adam kernel)."""
+        if self._deferred:
+            self._deferred = False
+            self._update()
+
+    def _update(self):
+        if self.pre_update_hook is not None:
+            self.pre_update_hook(self)
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
             items, steps = [], []
@@ -117,7 +143,6 @@ class FusedAdam(torch.optim.Adam):
             self._dev_step = before + 1
             self._last = (steps, [p for p, _, _, _ in items])
             self._bump(steps, self._last[1])
-        return loss
 
     @staticmethod
     def _bump(steps, params):

@@ -291,6 +291,7 @@ class Run:
 
     def __init__(self):
         self.Y, self.MR, self.XP = {}, {}, {}
+        self.stats_hw = {}     # conv node -> pixel count when MR holds raw sums (bf16 mode), absent = finalised
         self.xp_of_node = {}
         self.plain = {}        # act id -> (padded tensor, pad): where a residual can be read from
         self.ext = {}          # act id -> dense NHWC tensor (external inputs, z)
@@ -316,7 +317,8 @@ class Plan:
             xp = torch.empty(shape, dtype=dtype, device=src.device)
             mr = run.MR[act.producer] if act.norm else None
             resbuf, off = run.plain[act.res.id] if act.res is not None else (None, 0)
-            ops.xform_fwd(src, act.c, xp, mode, pad, mr, act.act, resbuf, off)
+            ops.xform_fwd(src, act.c, xp, mode, pad, mr, act.act, resbuf, off,
+                          stats_hw=run.stats_hw.get(act.producer, 0) if act.norm else 0)
             run.XP[key] = xp
             if mode == L.MODE_PLAIN and act.id not in run.plain:
                 run.plain[act.id] = (xp, pad)
@@ -368,7 +370,9 @@ class Plan:
                 if a0.norm and dtype == torch.bfloat16:
                     acc = stat_arena[stat_off[node]:stat_off[node] + n * node.spec.co * 2]
                     ops.conv_fwd(node.spec, xp, pc.wk, bias, y, acc, node.pre_act)
-                    run.MR[node] = ops.in_finalize(acc, n * node.spec.co, a0.h * a0.w, torch.empty_like(acc))
+                    # raw {sum, sum^2}: the consumers derive mean / rstd on load (stats_hw), no finalize launch
+                    run.MR[node] = acc
+                    run.stats_hw[node] = a0.h * a0.w
                 else:
                     ops.conv_fwd(node.spec, xp, pc.wk, bias, y, None, node.pre_act)
                     if a0.norm:
@@ -523,7 +527,8 @@ class Plan:
                     continue          # dead branch: nothing downstream needs this layer's gradient
                 a0, spec, holder = node.out_acts[0], node.spec, node.holder
                 halo = spec.pkh - 1
-                dy = ops.zero_halo_(torch.empty(n, a0.h + 2 * halo, a0.w + 2 * halo, spec.out_c, dtype=dtype, device=dev), halo)
+                # the halo ring of dY is cleared by the gather kernel itself (clear_halo)
+                dy = torch.empty(n, a0.h + 2 * halo, a0.w + 2 * halo, spec.out_c, dtype=dtype, device=dev)
                 y = run.Y[node]
                 if y.dtype != dtype:          # fp32-stored final image in bf16 mode: no norm/act there
                     y = None
@@ -538,10 +543,13 @@ class Plan:
                     if gs_arena is None:      # per-(n,c) reduction buffers of all normalised layers: one clear
                         gs_arena = ops.zero_(torch.empty(gs_total, dtype=torch.float32, device=dev))
                     gs = gs_arena[gs_off[node]:gs_off[node] + n * spec.co * 2]
-                    ops.xform_bwd_gather(srcs, y, n, a0.h, a0.w, spec.out_c, dy, halo, mr, a0.act, node.pre_act, gs, None)
-                    ops.xform_bwd_norm(y, n, a0.h, a0.w, spec.out_c, dy, halo, mr, gs, node.pre_act, dbias)
+                    shw = run.stats_hw.get(node, 0)
+                    ops.xform_bwd_gather(srcs, y, n, a0.h, a0.w, spec.out_c, dy, halo, mr, a0.act, node.pre_act, gs, None,
+                                         stats_hw=shw, clear_halo=True)
+                    ops.xform_bwd_norm(y, n, a0.h, a0.w, spec.out_c, dy, halo, mr, gs, node.pre_act, dbias, stats_hw=shw)
                 else:
-                    ops.xform_bwd_gather(srcs, y, n, a0.h, a0.w, spec.out_c, dy, halo, None, a0.act, node.pre_act, None, dbias)
+                    ops.xform_bwd_gather(srcs, y, n, a0.h, a0.w, spec.out_c, dy, halo, None, a0.act, node.pre_act, None, dbias,
+                                         clear_halo=True)
                 xp = run.xp_of_node[node]
                 if want_w:
                     ops.conv_wgrad(spec, xp, dy, dw)       # accumulates; added to .grad by flush_grads()
