@@ -75,6 +75,8 @@ int vcg_conv_fwd_simt(const vcg_conv_desc*, int, const void*, const void*, const
 int vcg_conv_wgrad_simt(const vcg_conv_desc*, int, const void*, const void*, int, int, float*, cudaStream_t);
 int vcg_conv_wgrad_thin(const vcg_conv_desc*, const void*, const void*, int, int, float*, cudaStream_t);
 bool vcg_wgrad_thin_supported(const vcg_conv_desc*);
+int vcg_conv_wgrad_fold(const vcg_conv_desc*, const void*, const void*, int, int, float*, cudaStream_t);
+bool vcg_wgrad_fold_supported(const vcg_conv_desc*, int, int);
 
 static bool force_simt() {
   static int v = -1;
@@ -103,7 +105,11 @@ extern "C" int vcg_conv_wgrad(const vcg_conv_desc* d, const void* x, const void*
   // into 64-pixel TMA boxes (inputs smaller than 256x256) stay on the SIMT kernel
   const int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
   const bool tileable = wo >= 64 ? (wo % 64 == 0) : (64 % wo == 0 && ho % (64 / wo) == 0);
-  // bf16 mode, cout <= 4 (the 64->3 output convolution): register-blocked FFMA kernel (M=3 is no tcgen05 shape)
+  // the two 7x7 image-side layers (64->3 and 3->64): horizontal taps folded into N, row pairs stacked into M
+  static const bool no_wfold = getenv("VCG_NO_WFOLD") && getenv("VCG_NO_WFOLD")[0] == '1';      // A/B timing switch
+  if (d->dtype == VCG_BF16 && !force_simt() && !no_wfold && vcg_wgrad_fold_supported(d, dy_halo, dy_c))
+    return vcg_conv_wgrad_fold(d, x, dy, dy_halo, dy_c, dw, stream);
+  // bf16 mode, cout <= 4 (the 64->3 output convolution) on maps the fold kernel does not take: HMMA kernel
   if (d->dtype == VCG_BF16 && !force_simt() && vcg_wgrad_thin_supported(d)) return vcg_conv_wgrad_thin(d, x, dy, dy_halo, dy_c, dw, stream);
   if (d->dtype == VCG_F32 || force_simt() || d->cout < 16 || !tileable)
     return vcg_conv_wgrad_simt(d, d->dtype, x, dy, dy_halo, dy_c, dw, stream);
