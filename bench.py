@@ -259,13 +259,14 @@ def run_ours(args):
     tc_ms = sum(fam.get(k, [0, 0, 0])[1] for k in ("conv_fwd", "conv_dgrad"))
     tc_n = sum(fam.get(k, [0, 0, 0])[2] for k in ("conv_fwd", "conv_dgrad"))
     achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms else 0.0
-    traffic = None
+    traffic, traffic_of = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("conv_tc_kernel_dram_bytes_per_launch")
+    if os.path.exists(tpath):     # ncu --set full capture of one representative launch (committed evidence)
+        tj = json.load(open(tpath))
+        traffic, traffic_of = tj.get("conv_tc_kernel_dram_bytes_per_launch"), tj.get("launch")
     roofline = {"kernel": "conv_tc_kernel (tcgen05 implicit GEMM: forward + data-gradient launches)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tflops"], "traffic": traffic, "peak_source": pk["source"],
+                "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_of": traffic_of, "peak_source": pk["source"],
                 "launches_per_step": tc_n / max(1, args.steps), "share_of_step": tc_ms / ms,
                 "flops_per_launch": tc_flops / max(1, tc_n), "ms_per_launch": tc_ms / max(1, tc_n),
                 "families": {k: {"tflops": v[0] / (v[1] / 1e3) / 1e12 if v[1] else 0.0, "ms_per_step": v[1] / args.steps,
