@@ -38,8 +38,21 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int encode_tmap_impl(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                            const uint32_t* box, const char* what, CUtensorMapSwizzle swz);
+
 int vcg_encode_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, const char* what) {
+  return encode_tmap_impl(map, base, rank, dims, strides_bytes, box, what, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+// same without shared-memory swizzle: the box lands as plain contiguous rows (inner box = 16 bytes)
+int vcg_encode_tmap_linear(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, const char* what) {
+  return encode_tmap_impl(map, base, rank, dims, strides_bytes, box, what, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+static int encode_tmap_impl(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                            const uint32_t* box, const char* what, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   VCG_REQUIRE(fn, VCG_E_DRIVER, "%s: cuTensorMapEncodeTiled is not available from the driver", what);
   VCG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, VCG_E_INVALID, "%s: base pointer not 16-byte aligned", what);
@@ -48,7 +61,7 @@ int vcg_encode_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gd, gs,
-                  bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];

@@ -237,6 +237,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
   return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
          (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// K-major operand WITHOUT swizzle ("interleaved" canonical layout, cute ((8,m),(T,2)):((1T,SBO),(1,LBO))): rows of a
+// core matrix are 16 bytes apart, 8-row groups SBO apart, the two 16-byte K chunks of one K=16 step LBO apart.
+__device__ __forceinline__ uint64_t umma_desc_linear(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+         (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
 // instruction descriptor for kind::f16: bf16 x bf16 -> fp32 (cute::UMMA::InstrDescriptor bit layout)
 __host__ __device__ inline uint32_t umma_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
   return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ |
@@ -248,3 +254,5 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int m, int n, int a_mn_major
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
 int vcg_encode_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box, const char* what);
+int vcg_encode_tmap_linear(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box, const char* what);

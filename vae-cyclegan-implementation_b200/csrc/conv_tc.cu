@@ -32,6 +32,13 @@ struct ConvTcArgs {
   int kw, cchunks, kblocks;
   int bn, cout, out_c, act, stats, out_f32;
   int num_m_tiles, num_tiles, stages;
+  int rowwin;               // 1: 8-channel input: the A operand is the raw pixel row in shared memory read through an
+                            //    un-swizzled descriptor whose row pitch (16 B) equals the pixel pitch, so the
+                            //    (kw, c) window of every pixel overlaps its neighbours' IN SHARED MEMORY: one 2 KB
+                            //    TMA load per (tile, kh) instead of a 16 KB overlapping-stride box
+  int nacc;                 // TMEM accumulator stages (2: measured no gain from 4 or 8 on short-K tiles)
+  int epi2;                 // 1: staged epilogue (TMEM -> shared memory tile -> coalesced stores + statistics)
+  int bres;                 // 1: the whole filter (kblocks x BN x 64) is loaded once per CTA and stays in shared memory
   uint32_t idesc, a_tx_bytes;
   const float* bias;
   float* stats_acc;
@@ -39,6 +46,8 @@ struct ConvTcArgs {
 };
 
 constexpr int kAStageBytes = 16384;  // 128 rows x 128 B
+constexpr int kRowWinPix = 136;      // rowwin mode: 128 output pixels + 8 window pixels
+constexpr int kRowWinStage = 2304;   // 136 pixels x 16 B, rounded up to a multiple of 128 B
 constexpr int kThreads = 384;   // warps 0-2: TMA / MMA / TMEM alloc, 3: idle, 4-11: epilogue (2 per TMEM lane quadrant)
 
 // Sum over the 32 lanes of a warp of v[j] for each j: afterwards lane l holds column l in v[0].
@@ -55,6 +64,35 @@ __device__ __forceinline__ void transposed_warp_sum32(float (&v)[32], int lane) 
   }
 }
 
+// bias + activation on 32 accumulator columns.  The bias of the current n-tile sits in a warp-private shared-memory
+// copy (8 broadcast LDS.128 instead of 32 global loads), the activation switch is hoisted out of the element loop
+// and columns >= ncols (beyond the logical output channels) are zeroed: ~3 instructions per element instead of ~10
+// (short-K tiles are bound by the instruction count of this epilogue).
+__device__ __forceinline__ void bias_act32(float (&v)[32], const float* __restrict__ sb, int act, int ncols) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(sb + 4 * q);
+    v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+  }
+  if (act == VCG_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (act == VCG_ACT_LEAKY) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+  }
+  if (ncols < 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j >= ncols) v[j] = 0.f;
+  }
+}
+// warp-private copy of bias[n0 .. n0+bn) (zeros where there is no bias / beyond cout)
+__device__ __forceinline__ void load_bias_tile(float* sb, const float* __restrict__ bias, int n0, int bn, int cout, int lane) {
+  __syncwarp();
+  for (int i = lane; i < bn; i += 32) sb[i] = (bias && n0 + i < cout) ? __ldg(bias + n0 + i) : 0.f;
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcArgs p) {
@@ -64,17 +102,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = smem_raw + (base - raw);
   const int S = p.stages;
   const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * 128u;
-  const uint32_t stage_bytes = kAStageBytes + b_bytes;
-  const uint32_t bar0 = base + S * stage_bytes;           // full[S], empty[S], tfull[2], tempty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S * stage_bytes + (2 * S + 4) * 8);
+  // resident-filter mode (short K, one n-tile: the thin image-side layers, which are L2->SM bound): stages hold
+  // only the A tile and the filter k-blocks live behind them; otherwise every stage carries its own B tile
+  const uint32_t stage_bytes = p.rowwin ? kRowWinStage : (p.bres ? kAStageBytes : kAStageBytes + b_bytes);
+  const uint32_t bres0 = (base + S * stage_bytes + 1023u) & ~1023u;      // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t bres_bytes = p.bres ? static_cast<uint32_t>(p.kblocks) * b_bytes : 0u;
+  const int NA = p.nacc;
+  const uint32_t bar0 = bres0 + bres_bytes;               // full[S], empty[S], tfull[NA], tempty[NA], bready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar0 - base) + (2 * S + 2 * NA + 1) * 8);
+  const uint32_t bready_bar = bar0 + 8u * (2 * S + 2 * NA);
+  const uint32_t bias0 = bar0 + 1024u;                    // 8 epilogue warps x 256 floats: bias of the current n-tile
+  const uint32_t epi0 = bias0 + 8192u;                    // staged-epilogue area (tile, row table, reduction slab)
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + NA + a); };
 
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * p.bn) tmem_cols <<= 1;
+  while (tmem_cols < static_cast<uint32_t>(NA * p.bn)) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -82,7 +128,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    for (int a = 0; a < NA; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    mbar_init(bready_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -106,6 +153,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // instructions: issuing from inside an `if (lane == 0)` region costs an R2UR waterfall loop per instruction.
   if (warp == 0) {
     // ===================== TMA producer =====================
+    if (p.bres && tile_begin < tile_end) {
+      if (elect_one_sync()) {
+        mbar_expect_tx(bready_bar, bres_bytes);
+        for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(bres0 + kb * b_bytes, &tmB, bready_bar, kb * 64, 0);
+      }
+      __syncwarp();
+    }
     int stage = 0; uint32_t phase = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
@@ -117,10 +171,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
         if (elect_one_sync()) {
-          mbar_expect_tx(full_bar(stage), p.a_tx_bytes + b_bytes);
-          if (p.flat) tma_load_4d(sa, &tmA, full_bar(stage), q * 64, w0 + khi * p.wp + kwi, 0, img);
-          else        tma_load_4d(sa, &tmA, full_bar(stage), q * 64, w0 + kwi, h0 + khi, img);
-          tma_load_2d(sb, &tmB, full_bar(stage), kb * 64, n0);
+          mbar_expect_tx(full_bar(stage), p.bres ? p.a_tx_bytes : p.a_tx_bytes + b_bytes);
+          if (p.rowwin) {
+            if (p.flat) tma_load_4d(sa, &tmA, full_bar(stage), 0, w0 + khi * p.wp, 0, img);
+            else        tma_load_4d(sa, &tmA, full_bar(stage), 0, w0, h0 + khi, img);
+          } else if (p.flat) tma_load_4d(sa, &tmA, full_bar(stage), q * 64, w0 + khi * p.wp + kwi, 0, img);
+          else               tma_load_4d(sa, &tmA, full_bar(stage), q * 64, w0 + kwi, h0 + khi, img);
+          if (!p.bres) tma_load_2d(sb, &tmB, full_bar(stage), kb * 64, n0);
         }
         __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -131,6 +188,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+    if (p.bres && tile_begin < tile_end) mbar_wait(bready_bar, 0);
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tc_fence_after();
@@ -138,8 +196,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
-        const uint64_t ad = umma_desc_sw128(sa, 16, 1024), bd = umma_desc_sw128(sb, 16, 1024);
+        const uint32_t sa = base + stage * stage_bytes;
+        const uint32_t sb = p.bres ? bres0 + kb * b_bytes : sa + kAStageBytes;
+        // rowwin: row pitch 16 B (one pixel), 8-row groups 128 B apart, second K chunk = next pixel (+16 B)
+        const uint64_t ad = p.rowwin ? umma_desc_linear(sa, 16, 128) : umma_desc_sw128(sa, 16, 1024);
+        const uint64_t bd = umma_desc_sw128(sb, 16, 1024);
         if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
@@ -150,8 +211,116 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (elect_one_sync()) umma_commit(tfull_bar(as));
       __syncwarp();
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (++as == NA) { as = 0; aphase ^= 1u; }
     }
+  } else if (warp >= 4 && p.epi2) {
+    // ===================== staged epilogue (BN <= 128) =====================
+    // phase A: TMEM -> registers -> bias/activation -> output dtype -> 128 x BN tile in shared memory (16-byte chunks
+    //          XOR-swizzled by row so that both phases are bank-conflict free); the accumulator is released here.
+    // phase B: the tile leaves as fully coalesced 16-byte stores (a pixel's BN channels are contiguous in NHWC) and
+    //          the InstanceNorm sum / sum-of-squares are column sums over the STORED values, read back from the tile
+    //          (no warp-shuffle transposes); per-(image, channel) running sums stay in registers until the image
+    //          changes.  Direct per-thread stores touched 32 different lines per instruction and the shuffle
+    //          reductions cost ~250 instructions per 32 columns: tiles with short K were bound by this epilogue.
+    const int et = static_cast<int>(threadIdx.x) - 128;             // 0..255
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int row = quad * 32 + lane;
+    const int esz = p.out_f32 ? 4 : 2;
+    const int row_bytes = p.bn * esz, cpr = row_bytes >> 4;          // 16-byte chunks per tile row
+    uint8_t* stg = smem + (epi0 - base);
+    int* rowinfo = reinterpret_cast<int*>(stg + 128 * row_bytes);
+    float* red = reinterpret_cast<float*>(rowinfo + 128);
+    auto swz = [&](int k, int r) { return (k & ~7) | ((k ^ r) & 7); };
+    const int pairs = p.bn >> 1, groups = 256 / pairs, rpg = 128 / groups;
+    int as = 0; uint32_t aphase = 0;
+    float* sb = reinterpret_cast<float*>(smem + (bias0 - base)) + (warp - 4) * 256;
+    int cur_n0 = -1;
+    float run = 0.f;                // thread et < 2*BN: running sum (et < BN) / sum of squares of channel n0 + et % BN
+    int run_img = -1, run_n0 = 0;
+    auto flush_stats = [&]() {
+      if (run_img >= 0 && et < 2 * p.bn) {
+        const int ch = run_n0 + (et % p.bn);
+        if (ch < p.cout) atomicAdd(p.stats_acc + (static_cast<size_t>(run_img) * p.cout + ch) * 2 + et / p.bn, run);
+      }
+      run = 0.f;
+    };
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int m_tile = tile % p.num_m_tiles, n_tile = tile / p.num_m_tiles;
+      const int img = m_tile / tiles_per_img, rem = m_tile % tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
+      const int n0 = n_tile * p.bn;
+      if (p.stats && (img != run_img || n0 != run_n0)) { flush_stats(); run_img = img; run_n0 = n0; }
+      int h, w; bool valid;
+      if (p.flat) { const int f = w0 + row; h = f / p.wp; w = f - h * p.wp; valid = (h < p.ho) && (w < p.wo); }
+      else { const int hh = row / p.tw; h = h0 + hh; w = w0 + (row - hh * p.tw);
+             valid = (row < p.tw * p.th) && (h < p.ho) && (w < p.wo); }
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.bn);
+      uint8_t* srow = stg + row * row_bytes;
+      if (n0 != cur_n0) { load_bias_tile(sb, p.bias, n0, p.bn, p.cout, lane); cur_n0 = n0; }
+#pragma unroll 1
+      for (int c0 = half * 32; c0 < p.bn; c0 += 64) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        bias_act32(v, sb + c0, p.act, valid ? p.cout - (n0 + c0) : 0);
+        if (p.out_f32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(srow + swz(c0 / 4 + j, row) * 16) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            __nv_bfloat162* hp2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hp2[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(srow + swz(c0 / 8 + j, row) * 16) = pk;
+          }
+        }
+      }
+      if (half == 0) rowinfo[row] = valid ? static_cast<int>((static_cast<size_t>(img) * p.ho + h) * p.wo + w) : -1;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));          // accumulator drained
+      if (++as == NA) { as = 0; aphase ^= 1u; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // ---- phase B: coalesced stores
+      const int cpe = 16 / esz;                              // channels per 16-byte chunk
+      for (int idx = et; idx < 128 * cpr; idx += 256) {
+        const int r2 = idx / cpr, k = idx - r2 * cpr;
+        const int pi = rowinfo[r2];
+        const int col0 = n0 + k * cpe;
+        if (pi >= 0 && (col0 & ~7) < p.cout) {
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + r2 * row_bytes + swz(k, r2) * 16);
+          *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out) + (static_cast<size_t>(pi) * p.out_c + col0) * esz) = val;
+        }
+      }
+      // ---- statistics over the stored (rounded) values: thread = (channel pair, group of rows)
+      if (p.stats) {
+        const int cp = et % pairs, g = et / pairs;
+        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+        for (int r2 = g * rpg; r2 < (g + 1) * rpg; ++r2) {
+          const uint32_t wv = *reinterpret_cast<const uint32_t*>(stg + r2 * row_bytes + swz(cp >> 2, r2) * 16 + (cp & 3) * 4);
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv));
+          s1a += f.x; s1b += f.y; s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
+        }
+        red[(g * 2 + 0) * p.bn + 2 * cp] = s1a; red[(g * 2 + 0) * p.bn + 2 * cp + 1] = s1b;
+        red[(g * 2 + 1) * p.bn + 2 * cp] = s2a; red[(g * 2 + 1) * p.bn + 2 * cp + 1] = s2b;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // tile + row table free again; slab complete
+      if (p.stats && et < 2 * p.bn) {
+        const int which = et / p.bn, ch = et % p.bn;
+        float t = 0.f;
+        for (int g = 0; g < groups; ++g) t += red[(g * 2 + which) * p.bn + ch];
+        run += t;
+      }
+    }
+    if (p.stats) flush_stats();
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     // two epilogue warps per TMEM lane quadrant: warp (4+q) takes the even 32-column chunks, warp (8+q) the odd
@@ -165,6 +334,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int i = 0; i < 8; ++i) run1[i] = run2[i] = 0.f;
     int run_img = -1, run_n0 = 0;
+    float* sb = reinterpret_cast<float*>(smem + (bias0 - base)) + (warp - 4) * 256;
+    int cur_n0 = -1;
     auto flush_stats = [&]() {
       if (run_img >= 0) {
 #pragma unroll
@@ -190,6 +361,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       else { const int hh = row / p.tw; h = h0 + hh; w = w0 + (row - hh * p.tw);
              valid = (row < p.tw * p.th) && (h < p.ho) && (w < p.wo); }
       const size_t pix = (static_cast<size_t>(img) * p.ho + h) * p.wo + w;
+      if (n0 != cur_n0) { load_bias_tile(sb, p.bias, n0, p.bn, p.cout, lane); cur_n0 = n0; }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.bn);
@@ -213,16 +385,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(r[j]); v[j + 16] = 0.f; }
         }
         const int col0 = n0 + c0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          float x = v[j];
-          if (col < p.cout) {
-            if (p.bias) x += __ldg(p.bias + col);
-            x = act_apply(x, p.act);
-          } else x = 0.f;
-          v[j] = x;
-        }
+        bias_act32(v, sb + c0, p.act, p.cout - col0);
         if (valid) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -249,7 +412,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (++as == NA) { as = 0; aphase ^= 1u; }
     }
     if (p.stats) flush_stats();
   }
@@ -329,13 +492,29 @@ int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const 
     static const int exp_mn = (getenv("VCG_EXP_MN") && getenv("VCG_EXP_MN")[0] == '1') ? 1 : 0;
     a.idesc = umma_idesc_bf16(128, bn, exp_mn, exp_mn);
   }
-  const int stage_bytes = kAStageBytes + bn * 128;
-  int stages = (227 * 1024 - 2048) / stage_bytes;
-  if (stages > 8) stages = 8;
-  if (stages > a.kblocks) stages = a.kblocks;
+  // resident filter: one n-tile, many tiles per CTA, and the whole filter fits beside >= 4 A stages
+  static const bool no_bres = getenv("VCG_NO_BRES") && getenv("VCG_NO_BRES")[0] == '1';      // A/B timing switch
+  const size_t filt_bytes = static_cast<size_t>(a.kblocks) * bn * 128;
+  a.bres = (!no_bres && ntn == 1 && a.num_tiles >= 4 * sms && filt_bytes + 4 * kAStageBytes + 3072 + 8192 + 40960 <= 227 * 1024) ? 1 : 0;
+  // staged epilogue: needs a 128 x BN output tile (+ row table + reduction slab) in shared memory
+  static const bool no_epi2 = getenv("VCG_NO_EPI2") && getenv("VCG_NO_EPI2")[0] == '1';      // A/B timing switch
+  const int esz = out_f32 ? 4 : 2;
+  // measured (tools/bench_conv.py, B=64): BN=128 layers gain (256->128 @128^2 forward 1020 -> 1178 TFLOP/s); BN=64 tiles
+  // are bound by the MMA's shared-memory operand reads and the extra tile traffic costs 10 %, so they keep the
+  // direct epilogue
+  a.epi2 = (!no_epi2 && bn == 128 && !out_f32 && static_cast<long long>(d->n) * ho * wo < (1LL << 31)) ? 1 : 0;
+  a.nacc = 2;
+  const size_t epi_bytes = a.epi2 ? static_cast<size_t>(128) * bn * esz + 512 + 4096 : 0;
+  static const bool no_rowwin = getenv("VCG_NO_ROWWIN") && getenv("VCG_NO_ROWWIN")[0] == '1';      // A/B timing switch
+  a.rowwin = (!no_rowwin && a.bres && window && d->c == 8 && d->kwc_pad == 64 && a.tw == 128 && a.th == 1) ? 1 : 0;
+  if (a.rowwin) a.a_tx_bytes = kRowWinPix * 16;
+  const int stage_bytes = a.rowwin ? kRowWinStage : (a.bres ? kAStageBytes : kAStageBytes + bn * 128);
+  int stages = static_cast<int>((227 * 1024 - 3072 - 8192 - (a.bres ? filt_bytes : 0) - epi_bytes) / stage_bytes);
+  if (stages > (a.rowwin ? 16 : 8)) stages = a.rowwin ? 16 : 8;
+  if (stages > a.kblocks && !a.bres) stages = a.kblocks;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 2048;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + (a.bres ? filt_bytes : 0) + 3072 + 8192 + epi_bytes;
 
   // ---- tensor maps
   CUtensorMap tmA, tmB;
@@ -357,7 +536,15 @@ int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const 
     strides[0] = pix_stride; strides[1] = row_stride; strides[2] = img_stride;
     box[0] = 64; box[1] = a.tw; box[2] = a.th; box[3] = 1;
   }
-  int rc = vcg_encode_tmap(&tmA, x, 4, dims, strides, box, "conv_tc A");
+  int rc;
+  if (a.rowwin) {
+    // plain (un-swizzled) map over the 8-channel pixels: box = 136 consecutive pixels of one row (flat: of the image)
+    dims[0] = 8; box[0] = 8; box[1] = kRowWinPix;
+    dims[1] = a.flat ? static_cast<uint64_t>(d->hp) * d->wp : static_cast<uint64_t>(d->wp);
+    rc = vcg_encode_tmap_linear(&tmA, x, 4, dims, strides, box, "conv_tc A (row window)");
+  } else {
+    rc = vcg_encode_tmap(&tmA, x, 4, dims, strides, box, "conv_tc A");
+  }
   if (rc) return rc;
   const uint64_t ktot = static_cast<uint64_t>(d->kh) * d->kwc_pad;
   uint64_t bdims[2] = {ktot, static_cast<uint64_t>(d->cout_pad)};
