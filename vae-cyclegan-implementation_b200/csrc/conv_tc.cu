@@ -438,9 +438,6 @@ static void pick_box(int wo, int ho, int* tw, int* th) {
 bool vcg_conv_fold_supported(const vcg_conv_desc* d, bool has_stats);
 int vcg_conv_fwd_tc_fold(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y, int out_f32,
                          cudaStream_t stream);
-bool vcg_conv_rows_supported(const vcg_conv_desc* d, bool has_stats);
-int vcg_conv_fwd_tc_rows(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y, int out_f32,
-                         cudaStream_t stream);
 
 int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                     float* stats, int out_f32, cudaStream_t stream) {
@@ -449,8 +446,6 @@ int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const 
   // into N, input rows streamed once through a ring of TMEM accumulators (conv_tc_fold.cu)
   static const bool no_fold = getenv("VCG_NO_FOLD") && getenv("VCG_NO_FOLD")[0] == '1';      // A/B timing switch
   if (!no_fold && vcg_conv_fold_supported(d, d->stats && stats)) return vcg_conv_fwd_tc_fold(d, x, w, bias, y, out_f32, stream);
-  // remaining thin-output shapes: multi-row blocks with a resident filter (conv_tc_rows.cu)
-  if (vcg_conv_rows_supported(d, d->stats && stats)) return vcg_conv_fwd_tc_rows(d, x, w, bias, y, out_f32, stream);
   VCG_REQUIRE(d->c % 8 == 0 && d->kwc_pad % 64 == 0 && d->cout_pad % 16 == 0 && d->out_c % 8 == 0,
               VCG_E_UNSUPPORTED, "conv_tc: unsupported channel geometry c=%d kwc_pad=%d cout_pad=%d cout=%d",
               d->c, d->kwc_pad, d->cout_pad, d->cout);

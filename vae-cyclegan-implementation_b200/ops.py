@@ -130,8 +130,8 @@ class ConvSpec:
 
 
 def _thin_kernel(dtype, c, cout, cout_pad, kh, kw, wo, has_stats):
-    """mirror of vcg_conv_fold_supported / vcg_conv_rows_supported (csrc/conv_tc_fold.cu, conv_tc_rows.cu): which
-    kernel a bf16 conv launch runs on ('fold', 'rows' or '' = conv_tc_kernel); used only to tag profiling records"""
+    """mirror of vcg_conv_fold_supported (csrc/conv_tc_fold.cu): which kernel a bf16 conv launch runs on
+    ('fold' or '' = conv_tc_kernel); used only to tag profiling records"""
     if dtype != torch.bfloat16 or has_stats or c % 64:
         return ""
     co8 = rup(cout, 8)
@@ -139,8 +139,6 @@ def _thin_kernel(dtype, c, cout, cout_pad, kh, kw, wo, has_stats):
     if cout <= 8 and wo >= 64 and kw in (2, 3, 7) and co8 <= cout_pad and bn <= 256 and min(8, 512 // bn) >= kh + 1 and \
             kh * (c // 64) * bn * 128 + 2 * kw * ((cout + 3) // 4) * 2048 + 2048 + 3 * 16384 <= 227 * 1024:
         return "fold"
-    if cout_pad <= 32 and wo >= 128 and kh * kw * (c // 64) * cout_pad * 128 + 4 * 16384 + 2048 <= 227 * 1024:
-        return "rows"
     return ""
 
 
