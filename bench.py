@@ -128,8 +128,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "full VAE-CycleGAN (CycleVAEGAN unpaired) 256x256 training step", "global_batch": args.global_batch,
-                   "cpu_sample_batch": args.cpu_batch},
+        "config": {"workload": "full VAE-CycleGAN (CycleVAEGAN unpaired: 2 VAE generators + 2 discriminators, cycle+KL+LSGAN) "
+                               "256x256 training step, global batch %d, per-GPU batch %d" % (args.global_batch, args.global_batch // max(1, args.gpus)),
+                   "global_batch": args.global_batch, "parallelism": f"dp{args.gpus}", "latent_dim": 64,
+                   "cpu_sample_batch": args.cpu_batch,
+                   "note": "reference arm: the reference's CPU path (oracle port, same ATen ops) on a bounded batch of the same workload"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -292,7 +295,7 @@ def run_ours(args):
         "final_metrics": {k: last[k] for k in ("G_loss", "D_loss", "loss_cycle", "loss_kl")},
     }
     if world == 1 and not args.no_cpu_baseline:
-        ts, threads = cpu_step_time(args.cpu_batch, 2, 1)
+        ts, threads = cpu_step_time(args.cpu_batch, 6, 1)      # ~11 s of CPU work on the box's 16 host threads
         v = args.cpu_batch * len(ts) / sum(ts)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"CycleVAEGAN(paired=False) training_step, batch {args.cpu_batch}, fp32, 1 warm-up + "

@@ -64,6 +64,7 @@ typedef struct vcg_wjob {
   int32_t t_kwc_pad;
   int32_t accumulate;        /* unpack: grad += */
   int32_t co_t, tiles_ci, tile0, ntiles;   /* filled by vcg_wjob_plan */
+  int32_t vec, reserved;                   /* filled by vcg_wjob_plan: 16-byte vector path (3x3, full 32x32 tiles) */
 } vcg_wjob;
 VCG_API int vcg_wjob_plan(vcg_wjob* jobs_host, int32_t njobs, int32_t* total_tiles);
 VCG_API int vcg_wpack_multi(int32_t dtype, const vcg_wjob* jobs_dev, int32_t njobs, int32_t total_tiles, void* stream);

@@ -85,6 +85,7 @@ struct WJob {
   int t_kwc_pad;        // row length per tap row of packed_t
   int accumulate;       // unpack: grad += instead of grad =
   int co_t, tiles_ci, tile0, ntiles;
+  int vec, reserved;
 };
 
 constexpr int kWTileFloats = 10240;   // 40 KB: 32 x 32 x 9(+1) fp32 for 3x3 filters
@@ -133,6 +134,139 @@ __device__ __forceinline__ void build_tap_tables(const WpArgs& p, int t_kwc, int
   }
 }
 
+// ---- 16-byte vector path (3x3 filters, 32 co x 32 ci tiles).  Shared tile s[co_l][ci_l * 9 + tap] with an ODD row
+// pitch (289 floats) so that reading 8 output channels of one (ci, tap) is conflict free.  A lane owns 8 channels of a
+// packed row: PLAIN cil = part*8 + i;  UNSHUFFLE cil = 4*i + part (those map to 8 consecutive physical channels).
+constexpr int kVecPitch = 289;
+
+__device__ __forceinline__ int vec_cil(const WpArgs& p, int part, int i) {
+  return p.wmap == VCG_WMAP_UNSHUFFLE ? 4 * i + part : part * 8 + i;
+}
+__device__ __forceinline__ int vec_ph0(const WpArgs& p, int ci0, int part) {      // first physical channel of the lane's 8
+  return p.wmap == VCG_WMAP_UNSHUFFLE ? part * (p.ci / 4) + (ci0 >> 2) : ci0 + part * 8;
+}
+
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) { st8<float>(p, v); }
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) { st8<__nv_bfloat16>(p, v); }
+
+template <typename T>
+__device__ __forceinline__ void wpack_tile_vec(const WJob& jb, const WpArgs& p, int co0, int ci0, float* s_tile) {
+  const int tid = threadIdx.x;
+  // phase 1: 32 OIHW runs of 288 floats -> s[col][k]  (float4 loads, 4 in flight)
+  for (int e0 = tid; e0 < 32 * 72; e0 += 4 * 256) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * 256;
+      if (e < 32 * 72) {
+        const int col = e / 72, k4 = e - col * 72;
+        v[u] = *reinterpret_cast<const float4*>(jb.oihw + (static_cast<size_t>(co0 + col) * p.ci + ci0) * 9 + 4 * k4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * 256;
+      if (e < 32 * 72) {
+        const int col = e / 72, k4 = e - col * 72;
+        float* d = s_tile + col * kVecPitch + 4 * k4;
+        d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+      }
+    }
+  }
+  __syncthreads();
+  const int part = tid & 3, rlane = tid >> 2;           // 64 row slots per pass, 4 lanes (x 8 channels) per row
+  // phase 2a: forward layout rows (co, tap): 32 input channels
+  {
+    T* out = static_cast<T*>(jb.packed);
+    const int ph0 = vec_ph0(p, ci0, part);
+    for (int r = rlane; r < 32 * 9; r += 64) {
+      const int col = r / 9, tap = r - col * 9;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = s_tile[col * kVecPitch + vec_cil(p, part, i) * 9 + tap];
+      store8<T>(out + (static_cast<size_t>(co0 + col) * 3 + tap / 3) * p.kwc_pad + (tap % 3) * p.c_phys + ph0, v);
+    }
+  }
+  // phase 2b: data-gradient layout rows (physical ci, flipped tap): 32 output channels
+  if (jb.packed_t) {
+    T* outT = static_cast<T*>(jb.packed_t);
+    for (int r = rlane; r < 32 * 9; r += 64) {
+      const int cil = r / 9, tap = r - cil * 9;
+      const int ph = p.wmap == VCG_WMAP_UNSHUFFLE ? (cil & 3) * (p.ci / 4) + ((ci0 + cil) >> 2) : ci0 + cil;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = s_tile[(part * 8 + i) * kVecPitch + cil * 9 + tap];
+      store8<T>(outT + (static_cast<size_t>(ph) * 3 + (2 - tap / 3)) * jb.t_kwc_pad + (2 - tap % 3) * p.co_phys + co0 + part * 8, v);
+    }
+  }
+}
+
+__device__ __forceinline__ void wunpack_tile_vec(const WJob& jb, const WpArgs& p, int co0, int ci0, float* s_tile) {
+  const int tid = threadIdx.x;
+  const int part = tid & 3, rlane = tid >> 2;
+  // phase 1: packed fp32 rows (co, tap) x 8 channels per lane -> s[col][cil*9+tap]; accumulator re-zeroed
+  {
+    float* dwp = static_cast<float*>(jb.packed);
+    const int ph0 = vec_ph0(p, ci0, part);
+    for (int r0 = rlane; r0 < 32 * 9; r0 += 2 * 64) {
+      float4 a[2][2];
+      float* ptr[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int r = r0 + 64 * u;
+        ptr[u] = nullptr;
+        if (r < 32 * 9) {
+          const int col = r / 9, tap = r - col * 9;
+          ptr[u] = dwp + (static_cast<size_t>(co0 + col) * 3 + tap / 3) * p.kwc_pad + (tap % 3) * p.c_phys + ph0;
+          a[u][0] = *reinterpret_cast<const float4*>(ptr[u]);
+          a[u][1] = *reinterpret_cast<const float4*>(ptr[u] + 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (ptr[u]) {
+          const int r = r0 + 64 * u;
+          const int col = r / 9, tap = r - col * 9;
+          const float v[8] = {a[u][0].x, a[u][0].y, a[u][0].z, a[u][0].w, a[u][1].x, a[u][1].y, a[u][1].z, a[u][1].w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s_tile[col * kVecPitch + vec_cil(p, part, i) * 9 + tap] = v[i];
+          *reinterpret_cast<float4*>(ptr[u]) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(ptr[u] + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // phase 2: OIHW runs of 288 floats (float4 read-modify-write, 4 in flight)
+  const bool acc = jb.accumulate != 0;
+  for (int e0 = tid; e0 < 32 * 72; e0 += 4 * 256) {
+    float4 g[4];
+    float* gp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * 256;
+      gp[u] = nullptr;
+      if (e < 32 * 72) {
+        const int col = e / 72, k4 = e - col * 72;
+        gp[u] = jb.oihw + (static_cast<size_t>(co0 + col) * p.ci + ci0) * 9 + 4 * k4;
+        if (acc) g[u] = *reinterpret_cast<const float4*>(gp[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (gp[u]) {
+        const int e = e0 + u * 256;
+        const int col = e / 72, k4 = e - col * 72;
+        const float* sp = s_tile + col * kVecPitch + 4 * k4;
+        float4 o = make_float4(sp[0], sp[1], sp[2], sp[3]);
+        if (acc) { o.x += g[u].x; o.y += g[u].y; o.z += g[u].z; o.w += g[u].w; }
+        *reinterpret_cast<float4*>(gp[u]) = o;
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 wpack_multi_kernel(const WJob* __restrict__ jobs, int njobs) {
@@ -144,6 +278,7 @@ wpack_multi_kernel(const WJob* __restrict__ jobs, int njobs) {
   const int co0 = (t / jb.tiles_ci) * jb.co_t, ci0 = (t % jb.tiles_ci) * 32;
   const int nco = min(jb.co_t, p.co - co0), nci = min(32, p.ci - ci0);
   const int taps = p.kh * p.kw, ts = taps | 1;
+  if (jb.vec) { wpack_tile_vec<T>(jb, p, co0, ci0, s_tile); return; }
   build_tap_tables(p, jb.t_kwc_pad, t_fwd, t_bwd);
   // phase 1: OIHW runs (nci*taps contiguous floats per output channel) -> s[co_l][ci_l][tap]; 4 loads in flight
   const float* __restrict__ wsrc = jb.oihw;
@@ -207,6 +342,7 @@ wunpack_multi_kernel(const WJob* __restrict__ jobs, int njobs) {
   const int co0 = (t / jb.tiles_ci) * jb.co_t, ci0 = (t % jb.tiles_ci) * 32;
   const int nco = min(jb.co_t, p.co - co0), nci = min(32, p.ci - ci0);
   const int taps = p.kh * p.kw, ts = taps | 1;
+  if (jb.vec) { wunpack_tile_vec(jb, p, co0, ci0, s_tile); return; }
   build_tap_tables(p, 0, t_fwd, t_bwd);
   __syncthreads();
   // phase 1: packed fp32 accumulator rows (32 input channels of one (output channel, tap)) -> s[co_l][ci_l][tap];
@@ -336,6 +472,9 @@ extern "C" int vcg_wjob_plan(vcg_wjob* jobs_host, int32_t njobs, int32_t* total_
     jb.tiles_ci = (jb.ci + 31) / 32;
     jb.tile0 = tile0;
     jb.ntiles = ((jb.co + co_t - 1) / co_t) * jb.tiles_ci;
+    // 16-byte vector path: 3x3 filters, whole 32x32 tiles, channel runs of 8 on the packed side
+    jb.vec = (taps == 9 && co_t == 32 && jb.ci % 32 == 0 && jb.co % 32 == 0 && jb.wmap != VCG_WMAP_S2D &&
+              jb.c_phys == jb.ci && jb.co_phys % 8 == 0 && jb.kwc_pad % 8 == 0 && jb.t_kwc_pad % 8 == 0) ? 1 : 0;
     tile0 += jb.ntiles;
   }
   *total_tiles = tile0;

@@ -48,7 +48,7 @@ class XbwdDesc(C.Structure):
 class WJob(C.Structure):
     _fields_ = _fields("co", "ci", "kh", "kw", "wmap", "c_phys", "co_phys", "rows_pad", "pkh", "pkw", "kwc_pad",
                        "transpose_flip") + [("oihw", C.c_void_p), ("packed", C.c_void_p), ("packed_t", C.c_void_p)] + \
-        _fields("t_kwc_pad", "accumulate", "co_t", "tiles_ci", "tile0", "ntiles")
+        _fields("t_kwc_pad", "accumulate", "co_t", "tiles_ci", "tile0", "ntiles", "vec", "reserved")
 
 
 class VecJob(C.Structure):
