@@ -42,3 +42,9 @@ t = timeit(lambda: ops.wpack_multi(tp, dt))
 print(f"pack   {nparam / 1e6:.1f} M params: {t * 1e3:8.1f} us  {(4 + 2 + 2) * nparam / t / 1e6:7.0f} GB/s (tiles {tp[2]})")
 t = timeit(lambda: ops.wunpack_multi(tu))
 print(f"unpack {nparam / 1e6:.1f} M params: {t * 1e3:8.1f} us  {16 * nparam / t / 1e6:7.0f} GB/s")
+tw = ops.wjob_table([(sp, g, dw, None) for sp, g, dw in zip(specs, grads, dws)], ws[0].device, accumulate=False)
+t = timeit(lambda: ops.wunpack_multi(tw))
+print(f"unpack (write, no accumulate) {t * 1e3:8.1f} us  {12 * nparam / t / 1e6:7.0f} GB/s")
+flat = torch.empty(nparam, device="cuda")
+t = timeit(lambda: ops.zero_(flat))
+print(f"zero {nparam * 4 / 1e6:.0f} MB: {t * 1e3:8.1f} us  {4 * nparam / t / 1e6:7.0f} GB/s")

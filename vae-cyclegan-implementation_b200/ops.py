@@ -156,7 +156,7 @@ def _to_device_bytes(carray, device):
     return torch.from_numpy(np.frombuffer(bytes(carray), dtype=np.uint8).copy()).to(device)
 
 
-def wjob_table(entries, device):
+def wjob_table(entries, device, accumulate=True):
     """entries: list of (spec, oihw fp32 tensor, packed fwd tensor, packed data-gradient tensor or None).
     Returns (device byte tensor holding the vcg_wjob array, njobs, total_tiles) for vcg_wpack_multi /
     vcg_wunpack_multi; build once and cache (the pointers must stay valid)."""
@@ -171,7 +171,7 @@ def wjob_table(entries, device):
         if packed_t is not None:
             assert tuple(packed_t.shape) == spec.packed_shape(True) and packed_t.dtype == packed.dtype
             arr[j].packed_t, arr[j].t_kwc_pad = packed_t.data_ptr(), spec.d_kwc_pad
-        arr[j].accumulate = 1
+        arr[j].accumulate = 1 if accumulate else 0
     total = C.c_int32(0)
     L.check(L.load().vcg_wjob_plan(arr, len(entries), C.byref(total)), "vcg_wjob_plan")
     return _to_device_bytes(arr, device), len(entries), int(total.value)
