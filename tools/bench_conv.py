@@ -18,6 +18,7 @@ SHAPES = [  # name, n, H(out), W(out), cin_phys, cout, k
     # thin layers at the batch-64 step (cin_phys = 8 for the 3-channel image)
     ("e0_b64", 64, 256, 256, 8, 64, 7), ("d5_b64", 64, 256, 256, 64, 3, 7), ("dU4_b64", 64, 256, 256, 32, 64, 3),
     ("dU3_b64", 64, 128, 128, 64, 128, 3), ("eD1_b64", 64, 128, 128, 256, 128, 3),
+    ("dU2_b64", 64, 64, 64, 128, 256, 3), ("dU1_b64", 64, 32, 32, 256, 512, 3),
     # probes: same output size as e0, different K
     ("p_k3", 64, 256, 256, 8, 64, 3), ("p_k5", 64, 256, 256, 8, 64, 5), ("p_c64k1", 64, 256, 256, 64, 64, 1), ("p_c64k3", 64, 256, 256, 64, 64, 3),
 ]

@@ -37,6 +37,9 @@ struct ConvTcArgs {
                             //    (kw, c) window of every pixel overlaps its neighbours' IN SHARED MEMORY: one 2 KB
                             //    TMA load per (tile, kh) instead of a 16 KB overlapping-stride box
   int nacc;                 // TMEM accumulator stages (2: measured no gain from 4 or 8 on short-K tiles)
+  int stats_smem;           // 1: column sums of the direct epilogue through a warp-private shared-memory transpose
+                            //    (8 STS.128 + 32 LDS + 64 FMA per 32x32 block instead of 62 shuffles + 124 selects +
+                            //    62 adds); used when the main loop is short, i.e. when the epilogue paces the kernel
   int epi2;                 // 1: staged epilogue (TMEM -> shared memory tile -> coalesced stores + statistics)
   int bres;                 // 1: the whole filter (kblocks x BN x 64) is loaded once per CTA and stays in shared memory
   uint32_t idesc, a_tx_bytes;
@@ -335,6 +338,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 8; ++i) run1[i] = run2[i] = 0.f;
     int run_img = -1, run_n0 = 0;
     float* sb = reinterpret_cast<float*>(smem + (bias0 - base)) + (warp - 4) * 256;
+    float* tr = reinterpret_cast<float*>(smem + (epi0 - base)) + (warp - 4) * (32 * 36);     // stats_smem: 32 x 36 floats per warp
     int cur_n0 = -1;
     auto flush_stats = [&]() {
       if (run_img >= 0) {
@@ -400,13 +404,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (p.stats && col0 < p.cout) {
-          float s1[32], s2[32];
+          if (p.stats_smem) {
+            // lane r parks its 32 values in row r (pitch 36 floats: conflict-free 16-byte stores), then lane j sums column j
+            __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { const float x = valid ? v[j] : 0.f; s1[j] = x; s2[j] = x * x; }
-          transposed_warp_sum32(s1, lane);
-          transposed_warp_sum32(s2, lane);
-          run1[ci] += s1[0];
-          run2[ci] += s2[0];
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(tr + lane * 36 + 4 * q) =
+                  valid ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) { const float x = tr[r * 36 + lane]; a1 += x; a2 = fmaf(x, x, a2); }
+            run1[ci] += a1;
+            run2[ci] += a2;
+          } else {
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float x = valid ? v[j] : 0.f; s1[j] = x; s2[j] = x * x; }
+            transposed_warp_sum32(s1, lane);
+            transposed_warp_sum32(s2, lane);
+            run1[ci] += s1[0];
+            run2[ci] += s2[0];
+          }
         }
       }
       tc_fence_before();
@@ -499,7 +518,9 @@ int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const 
   // direct epilogue
   a.epi2 = (!no_epi2 && bn == 128 && !out_f32 && static_cast<long long>(d->n) * ho * wo < (1LL << 31)) ? 1 : 0;
   a.nacc = 2;
-  const size_t epi_bytes = a.epi2 ? static_cast<size_t>(128) * bn * esz + 512 + 4096 : 0;
+  static const bool no_ssm = getenv("VCG_NO_STATS_SMEM") && getenv("VCG_NO_STATS_SMEM")[0] == '1';   // A/B timing switch
+  a.stats_smem = (!no_ssm && a.stats && !a.epi2 && a.kblocks <= 24) ? 1 : 0;   // measured: +13 % at 18 k-blocks, -3 % at 36
+  const size_t epi_bytes = a.epi2 ? static_cast<size_t>(128) * bn * esz + 512 + 4096 : (a.stats_smem ? 8 * 32 * 36 * 4 : 0);
   static const bool no_rowwin = getenv("VCG_NO_ROWWIN") && getenv("VCG_NO_ROWWIN")[0] == '1';      // A/B timing switch
   a.rowwin = (!no_rowwin && a.bres && window && d->c == 8 && d->kwc_pad == 64 && a.tw == 128 && a.th == 1) ? 1 : 0;
   if (a.rowwin) a.a_tx_bytes = kRowWinPix * 16;
