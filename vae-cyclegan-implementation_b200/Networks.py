@@ -383,15 +383,17 @@ class Autoencoder(_Composite):
             raise ValueError("Optimizer has not been configured yet.")
         x, y = self._xy(batch)
         loss = self.loss_fn(self(x), y)
-        if not bool(torch.isfinite(loss)):          # the reference's NaN/Inf guard (Networks.py:357-372)
+        # the reference's NaN/Inf guard (Networks.py:357-372) is a host synchronisation: it is kept in eager mode and
+        # skipped while the step is being captured into a CUDA graph (graph.GraphedStep), where no host read is legal
+        capturing = getattr(self, "_vcg_capture", None) is not None
+        if not capturing and not bool(torch.isfinite(loss)):
             self.optimizer.zero_grad()
             nan = float("nan")
             return {"nan_detected": True, "G_loss": nan, "loss_trans": nan, "total_loss": nan}
         self.optimizer.zero_grad()
         loss.backward()
         self.optimizer.step()
-        v = loss.item()
-        return {"G_loss": v, "loss_trans": v, "total_loss": v}
+        return self._items({"G_loss": loss, "loss_trans": loss, "total_loss": loss})
 
     def validation_step(self, batch):
         if self.loss_fn is None:
