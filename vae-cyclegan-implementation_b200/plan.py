@@ -221,7 +221,8 @@ def refresh_many(pcs, dtype):
         wk, wkT = pc.buffers(dtype)
         entries.append((pc.spec, w, wk, wkT))
     dev = entries[0][1].device
-    key = ("pack", dtype, tuple((e[1].data_ptr(), e[2].data_ptr(), e[3].data_ptr()) for e in entries))
+    # (pointers AND geometry: a freed model's addresses can be handed to differently shaped tensors later)
+    key = ("pack", dtype, tuple((e[0], e[1].data_ptr(), e[2].data_ptr(), e[3].data_ptr()) for e in entries))
     table = _cached_table(key, lambda: ops.wjob_table(entries, dev)) if cacheable else ops.wjob_table(entries, dev)
     ops.wpack_multi(table, dtype)
     for pc in stale:
@@ -248,10 +249,10 @@ def flush_grads():
             bent.append((pc.dbias, b.grad, pc.spec.co))
         pc.pending = pc.pending_bias = False
     dev = went[0][1].device
-    key = ("unpack", tuple((e[1].data_ptr(), e[2].data_ptr()) for e in went))
+    key = ("unpack", tuple((e[0], e[1].data_ptr(), e[2].data_ptr()) for e in went))
     ops.wunpack_multi(_cached_table(key, lambda: ops.wjob_table(went, dev)))
     if bent:
-        key = ("vec", tuple((e[0].data_ptr(), e[1].data_ptr()) for e in bent))
+        key = ("vec", tuple((e[0].data_ptr(), e[1].data_ptr(), e[2]) for e in bent))
         ops.vecflush_multi(_cached_table(key, lambda: ops.vecjob_table(bent, dev)))
 
 
