@@ -119,6 +119,8 @@ CONV_CASES = [  # (name, n, H, W, ci_in, co, k, wmap)
     # wide maps: thin-output forward / data-gradient shapes served by conv_tc_fold.cu (taps folded into N)
     ("d5wide", 2, 24, 160, 64, 3, 7, 0), ("e0wide", 1, 20, 140, 3, 64, 7, 0), ("dU4wide", 1, 40, 136, 32, 64, 3, 0),
     ("d5full", 1, 256, 256, 64, 3, 7, 0),
+    # odd number of 128-pixel tiles (CTA-pair kernel: the second CTA of the last pair has no tile)
+    ("oddtiles", 1, 24, 16, 128, 128, 3, 0),
 ]
 
 

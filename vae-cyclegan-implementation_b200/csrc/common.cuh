@@ -250,6 +250,52 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int m, int n, int a_mn_major
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ------------------------------------------------------------------ epilogue helpers shared by the conv kernels
+
+// Sum over the 32 lanes of a warp of v[j] for each j: afterwards lane l holds column l in v[0].
+__device__ __forceinline__ void transposed_warp_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = upper ? v[i + n / 2] : v[i];
+      const float send = upper ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
+// bias + activation on 32 accumulator columns.  The bias of the current n-tile sits in a warp-private shared-memory
+// copy (8 broadcast LDS.128 instead of 32 global loads), the activation switch is hoisted out of the element loop
+// and columns >= ncols (beyond the logical output channels) are zeroed: ~3 instructions per element instead of ~10
+// (short-K tiles are bound by the instruction count of this epilogue).
+__device__ __forceinline__ void bias_act32(float (&v)[32], const float* __restrict__ sb, int act, int ncols) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(sb + 4 * q);
+    v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+  }
+  if (act == VCG_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (act == VCG_ACT_LEAKY) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+  }
+  if (ncols < 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j >= ncols) v[j] = 0.f;
+  }
+}
+// warp-private copy of bias[n0 .. n0+bn) (zeros where there is no bias / beyond cout)
+__device__ __forceinline__ void load_bias_tile(float* sb, const float* __restrict__ bias, int n0, int bn, int cout, int lane) {
+  __syncwarp();
+  for (int i = lane; i < bn; i += 32) sb[i] = (bias && n0 + i < cout) ? __ldg(bias + n0 + i) : 0.f;
+  __syncwarp();
+}
+
+
 // ------------------------------------------------------------------ host: TMA descriptor encode
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
 int vcg_encode_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,

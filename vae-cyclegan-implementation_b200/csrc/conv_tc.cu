@@ -53,49 +53,6 @@ constexpr int kRowWinPix = 136;      // rowwin mode: 128 output pixels + 8 windo
 constexpr int kRowWinStage = 2304;   // 136 pixels x 16 B, rounded up to a multiple of 128 B
 constexpr int kThreads = 384;   // warps 0-2: TMA / MMA / TMEM alloc, 3: idle, 4-11: epilogue (2 per TMEM lane quadrant)
 
-// Sum over the 32 lanes of a warp of v[j] for each j: afterwards lane l holds column l in v[0].
-__device__ __forceinline__ void transposed_warp_sum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
-    const bool upper = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) {
-      const float keep = upper ? v[i + n / 2] : v[i];
-      const float send = upper ? v[i] : v[i + n / 2];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-}
-
-// bias + activation on 32 accumulator columns.  The bias of the current n-tile sits in a warp-private shared-memory
-// copy (8 broadcast LDS.128 instead of 32 global loads), the activation switch is hoisted out of the element loop
-// and columns >= ncols (beyond the logical output channels) are zeroed: ~3 instructions per element instead of ~10
-// (short-K tiles are bound by the instruction count of this epilogue).
-__device__ __forceinline__ void bias_act32(float (&v)[32], const float* __restrict__ sb, int act, int ncols) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 b = *reinterpret_cast<const float4*>(sb + 4 * q);
-    v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-  }
-  if (act == VCG_ACT_RELU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-  } else if (act == VCG_ACT_LEAKY) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
-  }
-  if (ncols < 32) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) if (j >= ncols) v[j] = 0.f;
-  }
-}
-// warp-private copy of bias[n0 .. n0+bn) (zeros where there is no bias / beyond cout)
-__device__ __forceinline__ void load_bias_tile(float* sb, const float* __restrict__ bias, int n0, int bn, int cout, int lane) {
-  __syncwarp();
-  for (int i = lane; i < bn; i += 32) sb[i] = (bias && n0 + i < cout) ? __ldg(bias + n0 + i) : 0.f;
-  __syncwarp();
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcArgs p) {
@@ -458,6 +415,10 @@ bool vcg_conv_fold_supported(const vcg_conv_desc* d, bool has_stats);
 int vcg_conv_fwd_tc_fold(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y, int out_f32,
                          cudaStream_t stream);
 
+bool vcg_conv2_supported(const vcg_conv_desc* d, int out_f32);
+int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y, float* stats,
+                     cudaStream_t stream);
+
 int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                     float* stats, int out_f32, cudaStream_t stream) {
   const int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
@@ -465,6 +426,7 @@ int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const 
   // into N, input rows streamed once through a ring of TMEM accumulators (conv_tc_fold.cu)
   static const bool no_fold = getenv("VCG_NO_FOLD") && getenv("VCG_NO_FOLD")[0] == '1';      // A/B timing switch
   if (!no_fold && vcg_conv_fold_supported(d, d->stats && stats)) return vcg_conv_fwd_tc_fold(d, x, w, bias, y, out_f32, stream);
+  if (vcg_conv2_supported(d, out_f32)) return vcg_conv_fwd_tc2(d, x, w, bias, y, stats, stream);
   VCG_REQUIRE(d->c % 8 == 0 && d->kwc_pad % 64 == 0 && d->cout_pad % 16 == 0 && d->out_c % 8 == 0,
               VCG_E_UNSUPPORTED, "conv_tc: unsupported channel geometry c=%d kwc_pad=%d cout_pad=%d cout=%d",
               d->c, d->kwc_pad, d->cout_pad, d->cout);

@@ -1,0 +1,455 @@
+// conv_tc2.cu -- CTA-pair (tcgen05 cta_group::2) variant of the implicit-GEMM convolution of conv_tc.cu for the wide
+// layers (64-channel-multiple inputs, BN = 128 / 256), sm_100a.
+//
+// With both operands in shared memory a single-CTA tcgen05.mma re-reads A (4 KB) and the whole B tile (BN x 32 B) per
+// K=16 step; below ~N = 256 that operand traffic, not the tensor pipe, paces the MMA.  A CTA pair
+// computes a 256 x BN tile: each CTA stages its own 128 rows of A and only HALF of the filter tile (BN/2 rows); the
+// pair's tensor cores share the two B halves, so the per-CTA shared-memory traffic drops from 4 KB + 32*BN to
+// 4 KB + 16*BN per step and a stage shrinks from 16 KB + 128*BN to 16 KB + 64*BN bytes (more pipeline stages).
+//
+// Protocol (the DeepGEMM / CUTLASS 2-SM pattern):
+//   * cluster of 2 CTAs; TMEM allocated with cta_group::2 by warp 2 of both CTAs;
+//   * both producers issue cta_group::2 TMA loads into their OWN shared memory that complete on the LEADER's full
+//     barrier (mbarrier address with the peer bit cleared); the leader expects the bytes of all four loads;
+//   * only the leader issues tcgen05.mma.cta_group::2 (M = 256); tcgen05.commit multicasts the arrival to the
+//     empty / accumulator-full barriers of both CTAs;
+//   * each CTA's epilogue warps drain their own 128 TMEM lanes; "accumulator empty" is collected on the leader's
+//     barrier (remote mbarrier.arrive from the second CTA).
+// Epilogue: bias + activation + InstanceNorm sum / sum-of-squares + bf16 NHWC store (the direct path of conv_tc.cu).
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace {
+
+struct Conv2Args {
+  int n_img, ho, wo, wp;
+  int tw, th, tiles_w, tiles_h;
+  int flat, kw, cchunks, kblocks;
+  int bn, cout, out_c, act, stats, epi2;
+  int num_m_tiles, num_pair_tiles, stages;      // pair tile = two consecutive m tiles x one n tile
+  uint32_t idesc, a_tx_bytes;
+  const float* bias;
+  float* stats_acc;
+  void* out;
+};
+
+constexpr int kAStageBytes = 16384;
+constexpr int kThreads = 384;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;     // shared::cluster address of the even (leader) CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in BOTH CTAs when all previously issued MMAs are done
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Conv2Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const int S = p.stages;
+  const uint32_t bh_bytes = static_cast<uint32_t>(p.bn / 2) * 128u;          // this CTA's half of the filter tile
+  const uint32_t stage_bytes = kAStageBytes + bh_bytes;
+  const uint32_t bar0 = base + S * stage_bytes;            // full[S], empty[S], tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S * stage_bytes + (2 * S + 4) * 8);
+  const uint32_t bias0 = bar0 + 1024u;
+  const uint32_t epi0 = bias0 + 8192u;                     // staged epilogue: 128 x BN bf16 tile, row table, slab
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+  const uint32_t rank = uniform_u32(cluster_ctarank());
+  const bool leader = rank == 0;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * p.bn) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }      // full: the leader's expect-tx arrive
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }   // tempty: 8 warps x 2 CTAs
+    fence_mbar_init();
+  }
+  cluster_sync_all();                                       // barrier inits visible to the peer before any remote use
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
+
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int m_pairs = (p.num_m_tiles + 1) / 2;
+  const int npairs = gridDim.x / 2, pair = blockIdx.x / 2;
+  const int per_pair = (p.num_pair_tiles + npairs - 1) / npairs;
+  const int tile_begin = pair * per_pair;
+  const int tile_end = min(p.num_pair_tiles, tile_begin + per_pair);
+  // pair tile t -> (m pair, n tile), m fastest; this CTA's m tile = 2 * m_pair + rank (may be one past the end)
+  auto decode = [&](int t, int& m_tile, int& n0, int& img, int& h0, int& w0) {
+    const int mp = t % m_pairs, n_tile = t / m_pairs;
+    m_tile = 2 * mp + static_cast<int>(rank);
+    n0 = n_tile * p.bn;
+    img = m_tile / tiles_per_img;
+    const int rem = m_tile - img * tiles_per_img;
+    h0 = (rem / p.tiles_w) * p.th; w0 = (rem % p.tiles_w) * p.tw;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int t = tile_begin; t < tile_end; ++t) {
+      int m_tile, n0, img, h0, w0;
+      decode(t, m_tile, n0, img, h0, w0);
+      int khi = 0, kwi = 0, q = 0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
+        const uint32_t lbar = full_bar(stage) & kPeerMask;       // the LEADER's full barrier
+        if (elect_one_sync()) {
+          // the leader expects the bytes of all four loads of the pair; the second CTA's loads only complete_tx there
+          if (leader) mbar_expect_tx(full_bar(stage), 2u * (p.a_tx_bytes + bh_bytes));
+          if (p.flat) tma2_load_4d(sa, &tmA, lbar, q * 64, w0 + khi * p.wp + kwi, 0, img);
+          else        tma2_load_4d(sa, &tmA, lbar, q * 64, w0 + kwi, h0 + khi, img);
+          tma2_load_2d(sb, &tmB, lbar, kb * 64, n0 + static_cast<int>(rank) * (p.bn / 2));
+        }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+        if (++q == p.cchunks) { q = 0; if (++kwi == p.kw) { kwi = 0; ++khi; } }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader) {
+      int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+      for (int t = tile_begin; t < tile_end; ++t) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.bn);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
+          const uint64_t ad = umma_desc_sw128(sa, 16, 1024), bd = umma_desc_sw128(sb, 16, 1024);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma2_bf16(d_tmem, ad + 2 * k, bd + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+            umma2_commit_both(empty_bar(stage));
+          }
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        if (elect_one_sync()) umma2_commit_both(tfull_bar(as));
+        __syncwarp();
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4 && p.epi2) {
+    // ===================== staged epilogue (BN = 128; see conv_tc.cu): TMEM -> bias/act -> bf16 tile in shared memory
+    // (16-byte chunks XOR-swizzled by row), then coalesced stores and column sums over the stored values
+    const int et = static_cast<int>(threadIdx.x) - 128;             // 0..255
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int row = quad * 32 + lane;
+    const int row_bytes = p.bn * 2, cpr = row_bytes >> 4;
+    uint8_t* stg = smem + (epi0 - base);
+    int* rowinfo = reinterpret_cast<int*>(stg + 128 * row_bytes);
+    float* red = reinterpret_cast<float*>(rowinfo + 128);
+    auto swz = [&](int k, int r) { return (k & ~7) | ((k ^ r) & 7); };
+    const int pairs = p.bn >> 1, groups = 256 / pairs, rpg = 128 / groups;
+    int as = 0; uint32_t aphase = 0;
+    float* sb = reinterpret_cast<float*>(smem + (bias0 - base)) + (warp - 4) * 256;
+    int cur_n0 = -1;
+    float run = 0.f;
+    int run_img = -1, run_n0 = 0;
+    auto flush_stats = [&]() {
+      if (run_img >= 0 && et < 2 * p.bn) {
+        const int ch = run_n0 + (et % p.bn);
+        if (ch < p.cout) atomicAdd(p.stats_acc + (static_cast<size_t>(run_img) * p.cout + ch) * 2 + et / p.bn, run);
+      }
+      run = 0.f;
+    };
+    for (int t = tile_begin; t < tile_end; ++t) {
+      int m_tile, n0, img, h0, w0;
+      decode(t, m_tile, n0, img, h0, w0);
+      const bool tile_ok = m_tile < p.num_m_tiles;
+      if (p.stats && tile_ok && (img != run_img || n0 != run_n0)) { flush_stats(); run_img = img; run_n0 = n0; }
+      int h, w; bool valid;
+      if (p.flat) { const int f = w0 + row; h = f / p.wp; w = f - h * p.wp; valid = (h < p.ho) && (w < p.wo); }
+      else { const int hh = row / p.tw; h = h0 + hh; w = w0 + (row - hh * p.tw);
+             valid = (row < p.tw * p.th) && (h < p.ho) && (w < p.wo); }
+      valid = valid && tile_ok;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.bn);
+      uint8_t* srow = stg + row * row_bytes;
+      if (n0 != cur_n0) { load_bias_tile(sb, p.bias, n0, p.bn, p.cout, lane); cur_n0 = n0; }
+#pragma unroll 1
+      for (int c0 = half * 32; c0 < p.bn; c0 += 64) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        bias_act32(v, sb + c0, p.act, valid ? p.cout - (n0 + c0) : 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 pk;
+          __nv_bfloat162* hp2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) hp2[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(srow + swz(c0 / 8 + j, row) * 16) = pk;
+        }
+      }
+      if (half == 0) rowinfo[row] = valid ? static_cast<int>((static_cast<size_t>(img) * p.ho + h) * p.wo + w) : -1;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int idx = et; idx < 128 * cpr; idx += 256) {
+        const int r2 = idx / cpr, k = idx - r2 * cpr;
+        const int pi = rowinfo[r2];
+        const int col0 = n0 + k * 8;
+        if (pi >= 0 && col0 < p.cout) {
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + r2 * row_bytes + swz(k, r2) * 16);
+          *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out) + (static_cast<size_t>(pi) * p.out_c + col0) * 2) = val;
+        }
+      }
+      if (p.stats) {
+        const int cp = et % pairs, g = et / pairs;
+        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+        for (int r2 = g * rpg; r2 < (g + 1) * rpg; ++r2) {
+          const uint32_t wv = *reinterpret_cast<const uint32_t*>(stg + r2 * row_bytes + swz(cp >> 2, r2) * 16 + (cp & 3) * 4);
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv));
+          s1a += f.x; s1b += f.y; s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
+        }
+        red[(g * 2 + 0) * p.bn + 2 * cp] = s1a; red[(g * 2 + 0) * p.bn + 2 * cp + 1] = s1b;
+        red[(g * 2 + 1) * p.bn + 2 * cp] = s2a; red[(g * 2 + 1) * p.bn + 2 * cp + 1] = s2b;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (p.stats && et < 2 * p.bn) {
+        const int which = et / p.bn, ch = et % p.bn;
+        float tsum = 0.f;
+        for (int g = 0; g < groups; ++g) tsum += red[(g * 2 + which) * p.bn + ch];
+        run += tsum;
+      }
+    }
+    if (p.stats) flush_stats();
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int row = quad * 32 + lane;
+    int as = 0; uint32_t aphase = 0;
+    float run1[8], run2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) run1[i] = run2[i] = 0.f;
+    int run_img = -1, run_n0 = 0;
+    float* sb = reinterpret_cast<float*>(smem + (bias0 - base)) + (warp - 4) * 256;
+    int cur_n0 = -1;
+    auto flush_stats = [&]() {
+      if (run_img >= 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int col = run_n0 + i * 32 + lane;
+          if ((i & 1) == half && i * 32 < p.bn && col < p.cout) {
+            float* dst = p.stats_acc + (static_cast<size_t>(run_img) * p.cout + col) * 2;
+            atomicAdd(dst, run1[i]);
+            atomicAdd(dst + 1, run2[i]);
+          }
+          run1[i] = run2[i] = 0.f;
+        }
+      }
+    };
+    for (int t = tile_begin; t < tile_end; ++t) {
+      int m_tile, n0, img, h0, w0;
+      decode(t, m_tile, n0, img, h0, w0);
+      const bool tile_ok = m_tile < p.num_m_tiles;
+      if (p.stats && tile_ok && (img != run_img || n0 != run_n0)) { flush_stats(); run_img = img; run_n0 = n0; }
+      int h, w; bool valid;
+      if (p.flat) { const int f = w0 + row; h = f / p.wp; w = f - h * p.wp; valid = (h < p.ho) && (w < p.wo); }
+      else { const int hh = row / p.tw; h = h0 + hh; w = w0 + (row - hh * p.tw);
+             valid = (row < p.tw * p.th) && (h < p.ho) && (w < p.wo); }
+      valid = valid && tile_ok;
+      const size_t pix = (static_cast<size_t>(img) * p.ho + h) * p.wo + w;
+      if (n0 != cur_n0) { load_bias_tile(sb, p.bias, n0, p.bn, p.cout, lane); cur_n0 = n0; }
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.bn);
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci) {
+        const int c0 = ci * 32;
+        if (c0 >= p.bn) break;
+        if ((ci & 1) != half) continue;
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const int col0 = n0 + c0;
+        bias_act32(v, sb + c0, p.act, p.cout - col0);
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < p.cout) {
+              float tt[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) tt[j] = v[g * 8 + j];
+              st8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_c + col, tt);
+            }
+          }
+        }
+        if (p.stats && col0 < p.cout) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float x = valid ? v[j] : 0.f; s1[j] = x; s2[j] = x * x; }
+          transposed_warp_sum32(s1, lane);
+          transposed_warp_sum32(s2, lane);
+          run1[ci] += s1[0];
+          run2[ci] += s2[0];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(as));      // both CTAs report to the leader's barrier
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    if (p.stats) flush_stats();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+}
+
+void pick_box2(int wo, int ho, int* tw, int* th) {
+  if (wo >= 128) { *tw = 128; *th = 1; return; }
+  *tw = wo;
+  int t = 128 / wo;
+  if (t > ho) t = ho;
+  if (t < 1) t = 1;
+  *th = t;
+}
+
+}  // namespace
+
+bool vcg_conv2_supported(const vcg_conv_desc* d, int out_f32) {
+  static const bool off = getenv("VCG_TC2") && getenv("VCG_TC2")[0] == '0';        // A/B timing switch
+  if (off || out_f32) return false;
+  if (d->c % 64 != 0 || d->kwc_pad != d->kw * d->c) return false;
+  if (d->cout_pad % 128 != 0 || d->cout != d->cout_pad || d->out_c != d->cout) return false;
+  const int kblocks = d->kh * (d->kwc_pad / 64);
+  return kblocks >= 8;
+}
+
+int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y, float* stats,
+                     cudaStream_t stream) {
+  const int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
+  Conv2Args a{};
+  a.n_img = d->n; a.ho = ho; a.wo = wo; a.wp = d->wp;
+  a.flat = d->flat ? 1 : 0; a.kw = d->kw;
+  a.cchunks = d->c / 64;
+  a.kblocks = d->kh * (d->kwc_pad / 64);
+  if (a.flat) {
+    a.tw = 128; a.th = 1; a.tiles_h = 1;
+    a.tiles_w = (ho * d->wp + 127) / 128;
+    a.a_tx_bytes = 128 * 128;
+  } else {
+    pick_box2(wo, ho, &a.tw, &a.th);
+    a.tiles_w = (wo + a.tw - 1) / a.tw;
+    a.tiles_h = (ho + a.th - 1) / a.th;
+    a.a_tx_bytes = static_cast<uint32_t>(a.tw * a.th) * 128u;
+  }
+  a.num_m_tiles = d->n * a.tiles_w * a.tiles_h;
+  int bn = d->cout_pad % 256 == 0 ? 256 : 128;
+  if (bn == 256 && static_cast<long long>((a.num_m_tiles + 1) / 2) * (d->cout_pad / 256) < vcg_num_sms() / 2) bn = 128;
+  a.bn = bn;
+  const int ntn = d->cout_pad / bn;
+  a.num_pair_tiles = ((a.num_m_tiles + 1) / 2) * ntn;
+  a.cout = d->cout; a.out_c = d->out_c; a.act = d->act; a.stats = (d->stats && stats) ? 1 : 0;
+  a.bias = bias; a.stats_acc = stats; a.out = y;
+  a.idesc = umma_idesc_bf16(256, bn, 0, 0);
+  static const bool no_epi2 = getenv("VCG_NO_EPI2") && getenv("VCG_NO_EPI2")[0] == '1';      // A/B timing switch
+  a.epi2 = (!no_epi2 && bn == 128 && static_cast<long long>(d->n) * ho * wo < (1LL << 31)) ? 1 : 0;
+  const int epi_bytes = a.epi2 ? 128 * bn * 2 + 512 + 4096 : 0;
+  const int stage_bytes = kAStageBytes + (bn / 2) * 128;
+  int stages = (227 * 1024 - 3072 - 8192 - epi_bytes) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > a.kblocks) stages = a.kblocks;
+  a.stages = stages;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 3072 + 8192 + epi_bytes;
+
+  CUtensorMap tmA, tmB;
+  const uint64_t es = 2;
+  const uint64_t pix_stride = static_cast<uint64_t>(d->c) * es, row_stride = d->wp * pix_stride, img_stride = d->hp * row_stride;
+  uint64_t dims[4], strides[3];
+  uint32_t box[4];
+  dims[0] = d->c;
+  if (a.flat) {
+    dims[1] = static_cast<uint64_t>(d->hp) * d->wp; dims[2] = 1; dims[3] = d->n;
+    strides[0] = pix_stride; strides[1] = img_stride; strides[2] = img_stride;
+    box[0] = 64; box[1] = 128; box[2] = 1; box[3] = 1;
+  } else {
+    dims[1] = d->wp; dims[2] = d->hp; dims[3] = d->n;
+    strides[0] = pix_stride; strides[1] = row_stride; strides[2] = img_stride;
+    box[0] = 64; box[1] = a.tw; box[2] = a.th; box[3] = 1;
+  }
+  int rc = vcg_encode_tmap(&tmA, x, 4, dims, strides, box, "conv_tc2 A");
+  if (rc) return rc;
+  const uint64_t ktot = static_cast<uint64_t>(d->kh) * d->kwc_pad;
+  uint64_t bdims[2] = {ktot, static_cast<uint64_t>(d->cout_pad)};
+  uint64_t bstr[1] = {ktot * es};
+  uint32_t bbox[2] = {64, static_cast<uint32_t>(bn / 2)};
+  rc = vcg_encode_tmap(&tmB, w, 2, bdims, bstr, bbox, "conv_tc2 B");
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    VCG_REQUIRE(e == cudaSuccess, VCG_E_CUDA, "conv_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int sms = vcg_num_sms();
+  int grid = (sms / 2) * 2;
+  if (grid > 2 * a.num_pair_tiles) grid = 2 * a.num_pair_tiles;
+  conv_tc2_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, a);
+  VCG_CHECK_LAUNCH("conv_tc2_kernel");
+  return VCG_OK;
+}
