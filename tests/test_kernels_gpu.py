@@ -121,6 +121,8 @@ CONV_CASES = [  # (name, n, H, W, ci_in, co, k, wmap)
     ("d5full", 1, 256, 256, 64, 3, 7, 0),
     # odd number of 128-pixel tiles (CTA-pair kernel: the second CTA of the last pair has no tile)
     ("oddtiles", 1, 24, 16, 128, 128, 3, 0),
+    # 80 pair tiles on 74 CTA pairs: the 6 left-over BN = 256 tiles are split into BN = 128 halves
+    ("tailsplit", 80, 16, 16, 64, 256, 3, 0),
 ]
 
 

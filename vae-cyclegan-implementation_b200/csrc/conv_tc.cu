@@ -41,6 +41,11 @@ struct ConvTcArgs {
                             //    (8 STS.128 + 32 LDS + 64 FMA per 32x32 block instead of 62 shuffles + 124 selects +
                             //    62 adds); used when the main loop is short, i.e. when the epilogue paces the kernel
   int epi2;                 // 1: staged epilogue (TMEM -> shared memory tile -> coalesced stores + statistics)
+  int epi3;                 // 1: BN <= 64 epilogue: one 32-column chunk per warp, InstanceNorm partial sums kept per lane in
+                            //    registers across tiles (cross-lane reduction only when the image changes)
+  int tstore;               // 1 (with epi3): the 128-pixel x 64-channel tile leaves through shared memory and one TMA store
+  int exp;                  // timing experiments (VCG_EXP_EPI): 1 no epilogue work, 2 no stores, 4 no statistics
+  int ashift;               // experiment: A rows loaded once per (kh, chunk), taps read through row-shifted descriptors
   int bres;                 // 1: the whole filter (kblocks x BN x 64) is loaded once per CTA and stays in shared memory
   uint32_t idesc, a_tx_bytes;
   const float* bias;
@@ -55,7 +60,7 @@ constexpr int kThreads = 384;   // warps 0-2: TMA / MMA / TMEM alloc, 3: idle, 4
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const ConvTcArgs p) {
+               const __grid_constant__ CUtensorMap tmO, const ConvTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -64,7 +69,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * 128u;
   // resident-filter mode (short K, one n-tile: the thin image-side layers, which are L2->SM bound): stages hold
   // only the A tile and the filter k-blocks live behind them; otherwise every stage carries its own B tile
-  const uint32_t stage_bytes = p.rowwin ? kRowWinStage : (p.bres ? kAStageBytes : kAStageBytes + b_bytes);
+  const uint32_t a_stage = p.ashift ? 17408u : static_cast<uint32_t>(kAStageBytes);
+  const uint32_t stage_bytes = p.rowwin ? kRowWinStage : (p.bres ? a_stage : a_stage + b_bytes);
   const uint32_t bres0 = (base + S * stage_bytes + 1023u) & ~1023u;      // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t bres_bytes = p.bres ? static_cast<uint32_t>(p.kblocks) * b_bytes : 0u;
   const int NA = p.nacc;
@@ -129,14 +135,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int khi = 0, kwi = 0, q = 0;
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
+        const uint32_t sa = base + stage * stage_bytes, sb = sa + a_stage;
+        const int kws = p.ashift ? 0 : kwi;
         if (elect_one_sync()) {
           mbar_expect_tx(full_bar(stage), p.bres ? p.a_tx_bytes : p.a_tx_bytes + b_bytes);
           if (p.rowwin) {
             if (p.flat) tma_load_4d(sa, &tmA, full_bar(stage), 0, w0 + khi * p.wp, 0, img);
             else        tma_load_4d(sa, &tmA, full_bar(stage), 0, w0, h0 + khi, img);
-          } else if (p.flat) tma_load_4d(sa, &tmA, full_bar(stage), q * 64, w0 + khi * p.wp + kwi, 0, img);
-          else               tma_load_4d(sa, &tmA, full_bar(stage), q * 64, w0 + kwi, h0 + khi, img);
+          } else if (p.flat) tma_load_4d(sa, &tmA, full_bar(stage), q * 64, w0 + khi * p.wp + kws, 0, img);
+          else               tma_load_4d(sa, &tmA, full_bar(stage), q * 64, w0 + kws, h0 + khi, img);
           if (!p.bres) tma_load_2d(sb, &tmB, full_bar(stage), kb * 64, n0);
         }
         __syncwarp();
@@ -157,9 +164,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t sa = base + stage * stage_bytes;
-        const uint32_t sb = p.bres ? bres0 + kb * b_bytes : sa + kAStageBytes;
+        const uint32_t sb = p.bres ? bres0 + kb * b_bytes : sa + a_stage;
         // rowwin: row pitch 16 B (one pixel), 8-row groups 128 B apart, second K chunk = next pixel (+16 B)
-        const uint64_t ad = p.rowwin ? umma_desc_linear(sa, 16, 128) : umma_desc_sw128(sa, 16, 1024);
+        uint64_t ad = p.rowwin ? umma_desc_linear(sa, 16, 128) : umma_desc_sw128(sa, 16, 1024);
+        if (p.ashift) {
+          const int kwi = (kb / p.cchunks) % p.kw;
+          ad = umma_desc_sw128(sa + kwi * 128, 16, 1024);
+          if (p.ashift == 1) ad |= static_cast<uint64_t>(kwi & 7) << 49;
+        }
         const uint64_t bd = umma_desc_sw128(sb, 16, 1024);
         if (elect_one_sync()) {
 #pragma unroll
@@ -281,6 +293,108 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (p.stats) flush_stats();
+  } else if (warp >= 4 && p.epi3) {
+    // ===================== thin-N epilogue (BN <= 64, one n-tile) =====================
+    // Short-K tiles with 64 output channels are paced by this code, not by the MMAs (measured: 64->64 1x1 @256^2 took
+    // 0.42 ms with the generic epilogue, 0.14 ms without any).  Two changes: (1) statistics: every lane adds its row's
+    // 32 values into per-lane partial sums that live in registers across ALL tiles of an image; the 32x32 transpose
+    // reduction runs once per image instead of once per tile; (2) stores: the bf16 tile is written to shared memory
+    // in the 128-byte-swizzle layout and leaves with ONE TMA tensor store (full 128-byte lines) instead of 4 STG.128
+    // per lane that each touch 32 different lines; three tile buffers, one named barrier per tile.
+    const int et = static_cast<int>(threadIdx.x) - 128;
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int row = quad * 32 + lane;
+    const int c0 = half * 32;
+    const bool has_chunk = c0 < p.bn;
+    float a1[32], a2[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a1[j] = a2[j] = 0.f;
+    int run_img = -1;
+    float* sb = reinterpret_cast<float*>(smem + (bias0 - base)) + (warp - 4) * 256;
+    load_bias_tile(sb, p.bias, 0, p.bn, p.cout, lane);
+    auto flush_stats = [&]() {
+      if (run_img >= 0 && has_chunk) {
+        transposed_warp_sum32(a1, lane);
+        transposed_warp_sum32(a2, lane);
+        const int col = c0 + lane;
+        if (col < p.cout) {
+          float* dst = p.stats_acc + (static_cast<size_t>(run_img) * p.cout + col) * 2;
+          atomicAdd(dst, a1[0]);
+          atomicAdd(dst + 1, a2[0]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a1[j] = a2[j] = 0.f;
+    };
+    int as = 0; uint32_t aphase = 0; int buf = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int m_tile = tile % p.num_m_tiles;
+      const int img = m_tile / tiles_per_img, rem = m_tile % tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * p.th, w0 = (rem % p.tiles_w) * p.tw;
+      if (p.stats && img != run_img) { flush_stats(); run_img = img; }
+      int h, w; bool valid;
+      if (p.flat) { const int f = w0 + row; h = f / p.wp; w = f - h * p.wp; valid = (h < p.ho) && (w < p.wo); }
+      else { const int hh = row / p.tw; h = h0 + hh; w = w0 + (row - hh * p.tw);
+             valid = (row < p.tw * p.th) && (h < p.ho) && (w < p.wo); }
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      uint32_t r[32];
+      if (has_chunk) {
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.bn + c0), r);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));          // accumulator is in registers: the next tile's MMAs may start
+      if (++as == NA) { as = 0; aphase ^= 1u; }
+      if (has_chunk && !(p.exp & 1)) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        bias_act32(v, sb + c0, p.act, valid ? p.cout - c0 : 0);
+        if (p.stats && !(p.exp & 4)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { a1[j] += v[j]; a2[j] = fmaf(v[j], v[j], a2[j]); }
+        }
+        if (p.tstore) {
+          uint8_t* srow = smem + (epi0 - base) + buf * 16384 + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            __nv_bfloat162* hp2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hp2[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(srow + (((half * 4 + j) ^ (row & 7)) << 4)) = pk;
+          }
+        } else if (valid && !(p.exp & 2)) {
+          const size_t pix = (static_cast<size_t>(img) * p.ho + h) * p.wo + w;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = c0 + g * 8;
+            if (col < p.cout) {
+              float t[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) t[j] = v[g * 8 + j];
+              st8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_c + col, t);
+            }
+          }
+        }
+      }
+      if (p.tstore) {
+        fence_proxy_async_smem();                           // generic-proxy tile writes -> visible to the TMA engine
+        // the store of two tiles ago has finished READING its buffer, which is the one the next tile writes
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0 && !(p.exp & 2)) {
+          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(epi0 + buf * 16384), "r"(0), "r"(w0), "r"(h0), "r"(img) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (++buf == 3) buf = 0;
+      }
+    }
+    if (p.stats) flush_stats();
+    if (p.tstore && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     // two epilogue warps per TMEM lane quadrant: warp (4+q) takes the even 32-column chunks, warp (8+q) the odd
@@ -326,6 +440,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.bn);
+      if (!(p.exp & 1))
 #pragma unroll
       for (int ci = 0; ci < 8; ++ci) {
         const int c0 = ci * 32;
@@ -347,7 +462,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int col0 = n0 + c0;
         bias_act32(v, sb + c0, p.act, p.cout - col0);
-        if (valid) {
+        if (valid && !(p.exp & 2)) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = col0 + g * 8;
@@ -360,7 +475,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        if (p.stats && col0 < p.cout) {
+        if (p.stats && col0 < p.cout && !(p.exp & 4)) {
           if (p.stats_smem) {
             // lane r parks its 32 values in row r (pitch 36 floats: conflict-free 16-byte stores), then lane j sums column j
             __syncwarp();
@@ -482,11 +597,23 @@ int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const 
   a.nacc = 2;
   static const bool no_ssm = getenv("VCG_NO_STATS_SMEM") && getenv("VCG_NO_STATS_SMEM")[0] == '1';   // A/B timing switch
   a.stats_smem = (!no_ssm && a.stats && !a.epi2 && a.kblocks <= 24) ? 1 : 0;   // measured: +13 % at 18 k-blocks, -3 % at 36
-  const size_t epi_bytes = a.epi2 ? static_cast<size_t>(128) * bn * esz + 512 + 4096 : (a.stats_smem ? 8 * 32 * 36 * 4 : 0);
+  static const bool no_epi3 = getenv("VCG_NO_EPI3") && getenv("VCG_NO_EPI3")[0] == '1';      // A/B timing switch
+  static const bool no_tstore = getenv("VCG_NO_TSTORE") && getenv("VCG_NO_TSTORE")[0] == '1';  // A/B timing switch
+  a.epi3 = (!no_epi3 && !a.epi2 && !out_f32 && ntn == 1 && (bn == 64 || bn == 32)) ? 1 : 0;
+  a.tstore = (a.epi3 && !no_tstore && !a.flat && bn == 64 && d->cout == 64 && d->out_c == 64 && a.tw == 128 && a.th == 1) ? 1 : 0;
+  if (a.epi3) a.stats_smem = 0;
+  const size_t epi_bytes = a.tstore ? 3 * 16384 : a.epi2 ? static_cast<size_t>(128) * bn * esz + 512 + 4096 : (a.stats_smem ? 8 * 32 * 36 * 4 : 0);
   static const bool no_rowwin = getenv("VCG_NO_ROWWIN") && getenv("VCG_NO_ROWWIN")[0] == '1';      // A/B timing switch
   a.rowwin = (!no_rowwin && a.bres && window && d->c == 8 && d->kwc_pad == 64 && a.tw == 128 && a.th == 1) ? 1 : 0;
   if (a.rowwin) a.a_tx_bytes = kRowWinPix * 16;
-  const int stage_bytes = a.rowwin ? kRowWinStage : (a.bres ? kAStageBytes : kAStageBytes + bn * 128);
+  { static const int ex = getenv("VCG_EXP_EPI") ? atoi(getenv("VCG_EXP_EPI")) : 0; a.exp = ex; }
+  {
+    const char* e = getenv("VCG_EXP_SHIFT");
+    a.ashift = (e && !window && !a.rowwin && a.tw == 128 && a.th == 1) ? atoi(e) : 0;
+    if (a.ashift) a.a_tx_bytes = 17408;
+  }
+  const int a_stage = a.ashift ? 17408 : kAStageBytes;
+  const int stage_bytes = a.rowwin ? kRowWinStage : (a.bres ? a_stage : a_stage + bn * 128);
   int stages = static_cast<int>((227 * 1024 - 3072 - 8192 - (a.bres ? filt_bytes : 0) - epi_bytes) / stage_bytes);
   if (stages > (a.rowwin ? 16 : 8)) stages = a.rowwin ? 16 : 8;
   if (stages > a.kblocks && !a.bres) stages = a.kblocks;
@@ -507,12 +634,12 @@ int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const 
     dims[1] = static_cast<uint64_t>(d->hp) * d->wp - (window ? (d->kw - 1) : 0);
     dims[2] = 1; dims[3] = d->n;
     strides[0] = pix_stride; strides[1] = img_stride; strides[2] = img_stride;
-    box[0] = 64; box[1] = 128; box[2] = 1; box[3] = 1;
+    box[0] = 64; box[1] = a.ashift ? 136 : 128; box[2] = 1; box[3] = 1;
   } else {
     dims[1] = window ? static_cast<uint64_t>(wo) : static_cast<uint64_t>(d->wp);
     dims[2] = d->hp; dims[3] = d->n;
     strides[0] = pix_stride; strides[1] = row_stride; strides[2] = img_stride;
-    box[0] = 64; box[1] = a.tw; box[2] = a.th; box[3] = 1;
+    box[0] = 64; box[1] = a.ashift ? 136 : a.tw; box[2] = a.th; box[3] = 1;
   }
   int rc;
   if (a.rowwin) {
@@ -537,8 +664,16 @@ int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const 
     VCG_REQUIRE(e == cudaSuccess, VCG_E_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  CUtensorMap tmO = tmA;                                   // placeholder unless the TMA-store epilogue is on
+  if (a.tstore) {
+    uint64_t od[4] = {static_cast<uint64_t>(d->out_c), static_cast<uint64_t>(wo), static_cast<uint64_t>(ho), static_cast<uint64_t>(d->n)};
+    uint64_t os[3] = {od[0] * es, od[0] * es * wo, od[0] * es * wo * ho};
+    uint32_t ob[4] = {64, 128, 1, 1};
+    rc = vcg_encode_tmap(&tmO, y, 4, od, os, ob, "conv_tc out");
+    if (rc) return rc;
+  }
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-  conv_tc_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, a);
+  conv_tc_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmO, a);
   VCG_CHECK_LAUNCH("conv_tc_kernel");
   return VCG_OK;
 }

@@ -26,9 +26,11 @@ struct Conv2Args {
   int n_img, ho, wo, wp;
   int tw, th, tiles_w, tiles_h;
   int flat, kw, cchunks, kblocks;
-  int bn, cout, out_c, act, stats, epi2;
+  int bn, cout, out_c, act, stats, epi2, skipa, exp;
   int num_m_tiles, num_pair_tiles, stages;      // pair tile = two consecutive m tiles x one n tile
-  uint32_t idesc, a_tx_bytes;
+  int tail_r, full_per_pair;                    // tail split (BN = 256): every pair runs full_per_pair whole tiles, then the
+                                                // tail_r left-over tiles are cut into two BN = 128 halves on 2 * tail_r pairs
+  uint32_t idesc, idesc_half, a_tx_bytes;
   const float* bias;
   float* stats_acc;
   void* out;
@@ -121,6 +123,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int per_pair = (p.num_pair_tiles + npairs - 1) / npairs;
   const int tile_begin = pair * per_pair;
   const int tile_end = min(p.num_pair_tiles, tile_begin + per_pair);
+  // work list of this pair: item i -> (pair tile, BN of this item, which 128-column half)
+  auto work = [&](int i, int& tt, int& bn_cur, int& nsub) -> bool {
+    nsub = 0; bn_cur = p.bn;
+    if (!p.tail_r) { tt = tile_begin + i; return tt < tile_end; }
+    if (i < p.full_per_pair) { tt = pair * p.full_per_pair + i; return true; }
+    if (i == p.full_per_pair && pair < 2 * p.tail_r) { tt = npairs * p.full_per_pair + (pair >> 1); bn_cur = 128; nsub = pair & 1; return true; }
+    return false;
+  };
   // pair tile t -> (m pair, n tile), m fastest; this CTA's m tile = 2 * m_pair + rank (may be one past the end)
   auto decode = [&](int t, int& m_tile, int& n0, int& img, int& h0, int& w0) {
     const int mp = t % m_pairs, n_tile = t / m_pairs;
@@ -134,9 +144,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0; uint32_t phase = 0;
-    for (int t = tile_begin; t < tile_end; ++t) {
+    for (int i = 0;; ++i) {
+      int t, bn_cur, nsub;
+      if (!work(i, t, bn_cur, nsub)) break;
       int m_tile, n0, img, h0, w0;
       decode(t, m_tile, n0, img, h0, w0);
+      n0 += nsub * 128;
+      const uint32_t bh_cur = static_cast<uint32_t>(bn_cur / 2) * 128u;
       int khi = 0, kwi = 0, q = 0;
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -144,10 +158,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t lbar = full_bar(stage) & kPeerMask;       // the LEADER's full barrier
         if (elect_one_sync()) {
           // the leader expects the bytes of all four loads of the pair; the second CTA's loads only complete_tx there
-          if (leader) mbar_expect_tx(full_bar(stage), 2u * (p.a_tx_bytes + bh_bytes));
+          const bool la = !(p.skipa && kwi != 0);       // timing experiment: skip the A loads of taps kw > 0
+          if (leader) mbar_expect_tx(full_bar(stage), 2u * ((la ? p.a_tx_bytes : 0u) + bh_cur));
+          if (la) {
           if (p.flat) tma2_load_4d(sa, &tmA, lbar, q * 64, w0 + khi * p.wp + kwi, 0, img);
           else        tma2_load_4d(sa, &tmA, lbar, q * 64, w0 + kwi, h0 + khi, img);
-          tma2_load_2d(sb, &tmB, lbar, kb * 64, n0 + static_cast<int>(rank) * (p.bn / 2));
+          }
+          // filter rows in 64-row boxes: this CTA's half of the n-tile is one (BN = 128) or two (BN = 256) of them
+          const int nrow = n0 + static_cast<int>(rank) * (bn_cur / 2);
+          tma2_load_2d(sb, &tmB, lbar, kb * 64, nrow);
+          if (bn_cur == 256) tma2_load_2d(sb + 8192, &tmB, lbar, kb * 64, nrow + 64);
         }
         __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -158,7 +178,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
       int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
-      for (int t = tile_begin; t < tile_end; ++t) {
+      for (int i = 0;; ++i) {
+        int t, bn_cur, nsub;
+        if (!work(i, t, bn_cur, nsub)) break;
+        const uint32_t idesc = bn_cur == p.bn ? p.idesc : p.idesc_half;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.bn);
@@ -169,7 +192,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint64_t ad = umma_desc_sw128(sa, 16, 1024), bd = umma_desc_sw128(sb, 16, 1024);
           if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma2_bf16(d_tmem, ad + 2 * k, bd + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma2_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             umma2_commit_both(empty_bar(stage));
           }
           __syncwarp();
@@ -216,6 +239,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       valid = valid && tile_ok;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      if (p.exp & 1) {                                   // timing experiment: no epilogue work at all
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tempty_bar(as));
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+        continue;
+      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.bn);
       uint8_t* srow = stg + row * row_bytes;
       if (n0 != cur_n0) { load_bias_tile(sb, p.bias, n0, p.bn, p.cout, lane); cur_n0 = n0; }
@@ -243,6 +273,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (lane == 0) mbar_arrive_leader(tempty_bar(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (!(p.exp & 2))
       for (int idx = et; idx < 128 * cpr; idx += 256) {
         const int r2 = idx / cpr, k = idx - r2 * cpr;
         const int pi = rowinfo[r2];
@@ -252,7 +283,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out) + (static_cast<size_t>(pi) * p.out_c + col0) * 2) = val;
         }
       }
-      if (p.stats) {
+      if (p.stats && !(p.exp & 4)) {
         const int cp = et % pairs, g = et / pairs;
         float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
         for (int r2 = g * rpg; r2 < (g + 1) * rpg; ++r2) {
@@ -297,9 +328,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     };
-    for (int t = tile_begin; t < tile_end; ++t) {
+    for (int i = 0;; ++i) {
+      int t, bn_cur, nsub;
+      if (!work(i, t, bn_cur, nsub)) break;
       int m_tile, n0, img, h0, w0;
       decode(t, m_tile, n0, img, h0, w0);
+      n0 += nsub * 128;
       const bool tile_ok = m_tile < p.num_m_tiles;
       if (p.stats && tile_ok && (img != run_img || n0 != run_n0)) { flush_stats(); run_img = img; run_n0 = n0; }
       int h, w; bool valid;
@@ -308,14 +342,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
              valid = (row < p.tw * p.th) && (h < p.ho) && (w < p.wo); }
       valid = valid && tile_ok;
       const size_t pix = (static_cast<size_t>(img) * p.ho + h) * p.wo + w;
-      if (n0 != cur_n0) { load_bias_tile(sb, p.bias, n0, p.bn, p.cout, lane); cur_n0 = n0; }
+      if (n0 != cur_n0) { load_bias_tile(sb, p.bias, n0, bn_cur, p.cout, lane); cur_n0 = n0; }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.bn);
 #pragma unroll
       for (int ci = 0; ci < 8; ++ci) {
         const int c0 = ci * 32;
-        if (c0 >= p.bn) break;
+        if (c0 >= bn_cur) break;
         if ((ci & 1) != half) continue;
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
@@ -407,6 +441,9 @@ int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const
   a.cout = d->cout; a.out_c = d->out_c; a.act = d->act; a.stats = (d->stats && stats) ? 1 : 0;
   a.bias = bias; a.stats_acc = stats; a.out = y;
   a.idesc = umma_idesc_bf16(256, bn, 0, 0);
+  a.idesc_half = umma_idesc_bf16(256, 128, 0, 0);
+  { static const int ex = getenv("VCG_EXP_EPI") ? atoi(getenv("VCG_EXP_EPI")) : 0; a.exp = ex; }
+  { static const bool sk = getenv("VCG_EXP_SKIPA") && getenv("VCG_EXP_SKIPA")[0] == '1'; a.skipa = sk ? 1 : 0; }
   static const bool no_epi2 = getenv("VCG_NO_EPI2") && getenv("VCG_NO_EPI2")[0] == '1';      // A/B timing switch
   a.epi2 = (!no_epi2 && bn == 128 && static_cast<long long>(d->n) * ho * wo < (1LL << 31)) ? 1 : 0;
   const int epi_bytes = a.epi2 ? 128 * bn * 2 + 512 + 4096 : 0;
@@ -437,7 +474,7 @@ int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const
   const uint64_t ktot = static_cast<uint64_t>(d->kh) * d->kwc_pad;
   uint64_t bdims[2] = {ktot, static_cast<uint64_t>(d->cout_pad)};
   uint64_t bstr[1] = {ktot * es};
-  uint32_t bbox[2] = {64, static_cast<uint32_t>(bn / 2)};
+  uint32_t bbox[2] = {64, 64};                              // 64 filter rows per box: one (BN = 128) or two (BN = 256) per CTA and stage
   rc = vcg_encode_tmap(&tmB, w, 2, bdims, bstr, bbox, "conv_tc2 B");
   if (rc) return rc;
   static bool attr_set = false;
@@ -449,6 +486,13 @@ int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const
   const int sms = vcg_num_sms();
   int grid = (sms / 2) * 2;
   if (grid > 2 * a.num_pair_tiles) grid = 2 * a.num_pair_tiles;
+  {
+    // wave quantisation (1024-channel layers at 16 x 16: 256 tiles on 74 pairs = 3.46 rounds): run the whole rounds as
+    // BN = 256 tiles and cut the left-over tiles into two BN = 128 halves, so the last round costs half a tile
+    static const bool no_tail = getenv("VCG_NO_TAIL") && getenv("VCG_NO_TAIL")[0] == '1';      // A/B timing switch
+    const int npairs = grid / 2, full = a.num_pair_tiles / npairs, rem = a.num_pair_tiles % npairs;
+    if (!no_tail && bn == 256 && full >= 1 && rem > 0 && 2 * rem <= npairs) { a.tail_r = rem; a.full_per_pair = full; }
+  }
   conv_tc2_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, a);
   VCG_CHECK_LAUNCH("conv_tc2_kernel");
   return VCG_OK;
