@@ -89,7 +89,9 @@ typedef struct vcg_conv_desc {
   int32_t out_c;      /* physical channels per output pixel */
   int32_t act;        /* VCG_ACT_* applied after bias, before stats */
   int32_t stats;      /* !=0: accumulate per-(n,cout) sum / sum-of-squares of the stored values */
-  int32_t flat;       /* !=0: tile the output in flattened input-pitch order (data-gradient) */
+  int32_t flat;       /* !=0: tile the output in flattened input-pitch order (data-gradient); 2: the caller also
+                         guarantees that the outer (kh-1, kw-1) border of x is zero, so taps that only see the
+                         border may be skipped (interior + ring schedule of conv_tc2.cu) */
   int32_t out_f32;    /* !=0: store y as fp32 even when dtype is VCG_BF16 (final image layer) */
 } vcg_conv_desc;
 

@@ -123,6 +123,8 @@ CONV_CASES = [  # (name, n, H, W, ci_in, co, k, wmap)
     ("oddtiles", 1, 24, 16, 128, 128, 3, 0),
     # 80 pair tiles on 74 CTA pairs: the 6 left-over BN = 256 tiles are split into BN = 128 halves
     ("tailsplit", 80, 16, 16, 64, 256, 3, 0),
+    # data gradient as interior tiles + border-ring tiles that batch images (partial image groups, odd group counts)
+    ("ring16", 9, 16, 16, 128, 128, 3, 0), ("ring16wide", 23, 16, 16, 256, 256, 3, 0), ("ring32", 5, 32, 32, 128, 256, 3, 0), ("ring64", 3, 64, 64, 128, 128, 3, 0),
 ]
 
 

@@ -10,12 +10,25 @@
 // Protocol (the DeepGEMM / CUTLASS 2-SM pattern):
 //   * cluster of 2 CTAs; TMEM allocated with cta_group::2 by warp 2 of both CTAs;
 //   * both producers issue cta_group::2 TMA loads into their OWN shared memory that complete on the LEADER's full
-//     barrier (mbarrier address with the peer bit cleared); the leader expects the bytes of all four loads;
+//     barrier (mbarrier address with the peer bit cleared); the leader expects the bytes of all loads of the pair;
 //   * only the leader issues tcgen05.mma.cta_group::2 (M = 256); tcgen05.commit multicasts the arrival to the
 //     empty / accumulator-full barriers of both CTAs;
 //   * each CTA's epilogue warps drain their own 128 TMEM lanes; "accumulator empty" is collected on the leader's
 //     barrier (remote mbarrier.arrive from the second CTA).
-// Epilogue: bias + activation + InstanceNorm sum / sum-of-squares + bf16 NHWC store (the direct path of conv_tc.cu).
+//
+// Work items.  Every pair walks a list of items; an item is (kind, pair tile, BN).  Three schedules:
+//   * plain: contiguous chunks of 256 x BN tiles (m fastest);
+//   * tail split (BN = 256): whole rounds of tiles, then the left-over tiles cut into two BN = 128 halves so the last
+//     round costs about half a tile (1024-channel layers at 16 x 16: 256 tiles on 74 pairs = 3.46 rounds);
+//   * interior + ring (data gradient of a 3 x 3 reflect-padded layer on a small map).  The data gradient is the full
+//     correlation of the zero-haloed dY with the flipped filter: (H, W) = (ho + 2, wo + 2) outputs per image.  Tiling
+//     that in flat input-pitch order computes 384 rows per 16 x 16 image for 324 outputs, and two thirds of the taps
+//     of the 68 border outputs multiply zero rows.  Here the ho x wo interior is tiled exactly (kind 0: 2 tiles per
+//     16 x 16 image, all 9 taps) and the border ring is computed by four cheap tile kinds that batch images in the
+//     TMA box and run only the 3 taps that can be non-zero: top / bottom row (box 64ch x W x 1 x tn images, taps
+//     kh = 2 / kh = 0) and left / right column (box 64ch x 1 x ho x tn, taps kw = 2 / kw = 0).
+// Epilogue: bias + activation + InstanceNorm sum / sum-of-squares + bf16 NHWC store (direct, or staged through shared
+// memory at BN = 128; see conv_tc.cu).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -23,17 +36,29 @@
 namespace {
 
 struct Conv2Args {
-  int n_img, ho, wo, wp;
+  int n_img, ho, wo, wp;                        // ho, wo: output rows / columns of the convolution
   int tw, th, tiles_w, tiles_h;
-  int flat, kw, cchunks, kblocks;
-  int bn, cout, out_c, act, stats, epi2, skipa, exp;
+  int flat, kh, kw, cchunks;
+  int bn, cout, out_c, act, stats, epi2;
   int num_m_tiles, num_pair_tiles, stages;      // pair tile = two consecutive m tiles x one n tile
-  int tail_r, full_per_pair;                    // tail split (BN = 256): every pair runs full_per_pair whole tiles, then the
-                                                // tail_r left-over tiles are cut into two BN = 128 halves on 2 * tail_r pairs
-  uint32_t idesc, idesc_half, a_tx_bytes;
+  int tail_r, full_per_pair;                    // tail split
+  int ring;                                     // 1: interior + ring schedule (num_pair_tiles = interior pair tiles)
+  int tn_tb, tn_lr, p_tb, p_lr, ring_pairs;     // images per ring box; pair tiles per ring side (x n tiles = ring_pairs)
+  uint32_t idesc, idesc_half, a_tx_bytes, tb_tx_bytes, lr_tx_bytes;
   const float* bias;
   float* stats_acc;
   void* out;
+};
+
+// one work item as seen by this CTA of the pair
+struct Item {
+  int kind;                 // 0: convolution tile; 1..4: ring top / bottom / left / right
+  int bn, n0;               // output columns of this item
+  int img, h0, w0;          // kind 0: image and tile origin; ring: first image of the box (h0 = w0 = 0)
+  int ok;                   // this CTA's m tile exists (odd counts: the last pair has one tile)
+  int kh_lo, kh_hi, kw_lo, kw_hi;   // taps that contribute
+  int ch, cw;               // input-coordinate origin of the A box for tap (0, 0)
+  uint32_t a_bytes;
 };
 
 constexpr int kAStageBytes = 16384;
@@ -78,14 +103,14 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Conv2Args p) {
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmTB, const __grid_constant__ CUtensorMap tmLR, const Conv2Args p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const int S = p.stages;
-  const uint32_t bh_bytes = static_cast<uint32_t>(p.bn / 2) * 128u;          // this CTA's half of the filter tile
-  const uint32_t stage_bytes = kAStageBytes + bh_bytes;
+  const uint32_t stage_bytes = kAStageBytes + static_cast<uint32_t>(p.bn / 2) * 128u;   // A tile + this CTA's half of B
   const uint32_t bar0 = base + S * stage_bytes;            // full[S], empty[S], tfull[2], tempty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S * stage_bytes + (2 * S + 4) * 8);
   const uint32_t bias0 = bar0 + 1024u;
@@ -96,12 +121,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
 
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
-  const uint32_t rank = uniform_u32(cluster_ctarank());
+  const int rank = static_cast<int>(uniform_u32(cluster_ctarank()));
   const bool leader = rank == 0;
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * p.bn) tmem_cols <<= 1;
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+    if (p.ring) { tma_prefetch_desc(&tmTB); tma_prefetch_desc(&tmLR); }
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }      // full: the leader's expect-tx arrive
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }   // tempty: 8 warps x 2 CTAs
@@ -123,69 +151,135 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int per_pair = (p.num_pair_tiles + npairs - 1) / npairs;
   const int tile_begin = pair * per_pair;
   const int tile_end = min(p.num_pair_tiles, tile_begin + per_pair);
-  // work list of this pair: item i -> (pair tile, BN of this item, which 128-column half)
-  auto work = [&](int i, int& tt, int& bn_cur, int& nsub) -> bool {
-    nsub = 0; bn_cur = p.bn;
-    if (!p.tail_r) { tt = tile_begin + i; return tt < tile_end; }
-    if (i < p.full_per_pair) { tt = pair * p.full_per_pair + i; return true; }
-    if (i == p.full_per_pair && pair < 2 * p.tail_r) { tt = npairs * p.full_per_pair + (pair >> 1); bn_cur = 128; nsub = pair & 1; return true; }
+  const int ring_full = p.num_pair_tiles / npairs, ring_left = p.num_pair_tiles % npairs;
+  const int ring_sides = 2 * p.p_tb + 2 * p.p_lr;           // ring pair tiles per n tile
+
+  // convolution tile t (m pair, n tile; m fastest) as seen by this CTA
+  auto conv_item = [&](int t, int bn_cur, int nsub, Item& it) {
+    const int mp = t % m_pairs, n_tile = t / m_pairs;
+    const int m_tile = 2 * mp + rank;
+    it.kind = 0; it.bn = bn_cur; it.n0 = n_tile * p.bn + nsub * 128;
+    it.ok = m_tile < p.num_m_tiles;
+    it.img = m_tile / tiles_per_img;
+    const int rem = m_tile - it.img * tiles_per_img;
+    it.h0 = (rem / p.tiles_w) * p.th; it.w0 = (rem % p.tiles_w) * p.tw;
+    it.kh_lo = 0; it.kh_hi = p.kh; it.kw_lo = 0; it.kw_hi = p.kw;
+    it.a_bytes = p.a_tx_bytes;
+    if (p.ring) { it.ch = it.h0 + 1; it.cw = it.w0 + 1; }              // interior of the (ho + 2) x (wo + 2) gradient
+    else if (p.flat) { it.ch = 0; it.cw = it.w0; }
+    else { it.ch = it.h0; it.cw = it.w0; }
+  };
+  // ring pair tile j: (n tile, side, image group)
+  auto ring_item = [&](int j, Item& it) {
+    const int n_tile = j / ring_sides;
+    const int r = j - n_tile * ring_sides;
+    int kind, g;
+    if (r < p.p_tb) { kind = 1; g = r; }
+    else if (r < 2 * p.p_tb) { kind = 2; g = r - p.p_tb; }
+    else if (r < 2 * p.p_tb + p.p_lr) { kind = 3; g = r - 2 * p.p_tb; }
+    else { kind = 4; g = r - 2 * p.p_tb - p.p_lr; }
+    const int tn = kind <= 2 ? p.tn_tb : p.tn_lr;
+    it.kind = kind; it.bn = p.bn; it.n0 = n_tile * p.bn;
+    it.img = (2 * g + rank) * tn; it.h0 = 0; it.w0 = 0;
+    it.ok = it.img < p.n_img;
+    it.kh_lo = 0; it.kh_hi = p.kh; it.kw_lo = 0; it.kw_hi = p.kw;
+    it.ch = 0; it.cw = 0;
+    // gradient row 0 only sees dY row 0 (tap kh = 2), row H-1 only dY's last row (tap kh = 0); same for the columns
+    if (kind == 1) { it.kh_lo = p.kh - 1; }
+    else if (kind == 2) { it.kh_hi = 1; it.ch = p.ho + 1; }
+    else if (kind == 3) { it.kw_lo = p.kw - 1; it.ch = 1; }
+    else { it.kw_hi = 1; it.ch = 1; it.cw = p.wo + 1; }
+    it.a_bytes = kind <= 2 ? p.tb_tx_bytes : p.lr_tx_bytes;
+  };
+  // i-th work item of this pair
+  auto work = [&](int i, Item& it) -> bool {
+    if (p.ring) {
+      if (i < ring_full) { conv_item(pair * ring_full + i, p.bn, 0, it); return true; }
+      int k = i - ring_full;
+      if (pair < ring_left) { if (k == 0) { conv_item(npairs * ring_full + pair, p.bn, 0, it); return true; } --k; }
+      // ring tiles (3 of 9 taps: a third of a tile) first fill the pairs without a left-over convolution tile, three
+      // each, then go round-robin over all pairs
+      const int spread = npairs - ring_left;
+      const int lim1 = ring_left > 0 ? min(p.ring_pairs, 3 * spread) : 0;
+      if (ring_left > 0 && pair >= ring_left) {
+        const int first = pair - ring_left;
+        const int n1 = first < lim1 ? (lim1 - first + spread - 1) / spread : 0;
+        if (k < n1) { ring_item(first + k * spread, it); return true; }
+        k -= n1;
+      }
+      const int j = lim1 + pair + k * npairs;
+      if (j >= p.ring_pairs) return false;
+      ring_item(j, it);
+      return true;
+    }
+    if (!p.tail_r) { const int t = tile_begin + i; if (t >= tile_end) return false; conv_item(t, p.bn, 0, it); return true; }
+    if (i < p.full_per_pair) { conv_item(pair * p.full_per_pair + i, p.bn, 0, it); return true; }
+    if (i == p.full_per_pair && pair < 2 * p.tail_r) { conv_item(npairs * p.full_per_pair + (pair >> 1), 128, pair & 1, it); return true; }
     return false;
   };
-  // pair tile t -> (m pair, n tile), m fastest; this CTA's m tile = 2 * m_pair + rank (may be one past the end)
-  auto decode = [&](int t, int& m_tile, int& n0, int& img, int& h0, int& w0) {
-    const int mp = t % m_pairs, n_tile = t / m_pairs;
-    m_tile = 2 * mp + static_cast<int>(rank);
-    n0 = n_tile * p.bn;
-    img = m_tile / tiles_per_img;
-    const int rem = m_tile - img * tiles_per_img;
-    h0 = (rem / p.tiles_w) * p.th; w0 = (rem % p.tiles_w) * p.tw;
+  // accumulator row -> output pixel
+  auto rowmap = [&](const Item& it, int row, size_t& pix) -> bool {
+    int img = it.img, h, w; bool valid;
+    if (it.kind == 0) {
+      if (p.flat && !p.ring) { const int f = it.w0 + row; h = f / p.wp; w = f - h * p.wp; valid = (h < p.ho) && (w < p.wo); }
+      else { const int hh = row / p.tw; h = it.h0 + hh; w = it.w0 + (row - hh * p.tw);
+             valid = (row < p.tw * p.th) && (h < p.ho) && (w < p.wo); }
+      valid = valid && it.ok;
+      if (p.ring) { pix = (static_cast<size_t>(img) * (p.ho + 2) + h + 1) * (p.wo + 2) + w + 1; return valid; }
+      pix = (static_cast<size_t>(img) * p.ho + h) * p.wo + w;
+      return valid;
+    }
+    const int H = p.ho + 2, W = p.wo + 2;
+    int nl;
+    if (it.kind <= 2) { nl = row / W; w = row - nl * W; h = it.kind == 1 ? 0 : H - 1; valid = nl < p.tn_tb; }
+    else { nl = row / p.ho; h = 1 + row - nl * p.ho; w = it.kind == 3 ? 0 : W - 1; valid = nl < p.tn_lr; }
+    img += nl;
+    pix = (static_cast<size_t>(img) * H + h) * W + w;
+    return valid && img < p.n_img;
   };
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0; uint32_t phase = 0;
     for (int i = 0;; ++i) {
-      int t, bn_cur, nsub;
-      if (!work(i, t, bn_cur, nsub)) break;
-      int m_tile, n0, img, h0, w0;
-      decode(t, m_tile, n0, img, h0, w0);
-      n0 += nsub * 128;
-      const uint32_t bh_cur = static_cast<uint32_t>(bn_cur / 2) * 128u;
-      int khi = 0, kwi = 0, q = 0;
-      for (int kb = 0; kb < p.kblocks; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
-        const uint32_t lbar = full_bar(stage) & kPeerMask;       // the LEADER's full barrier
-        if (elect_one_sync()) {
-          // the leader expects the bytes of all four loads of the pair; the second CTA's loads only complete_tx there
-          const bool la = !(p.skipa && kwi != 0);       // timing experiment: skip the A loads of taps kw > 0
-          if (leader) mbar_expect_tx(full_bar(stage), 2u * ((la ? p.a_tx_bytes : 0u) + bh_cur));
-          if (la) {
-          if (p.flat) tma2_load_4d(sa, &tmA, lbar, q * 64, w0 + khi * p.wp + kwi, 0, img);
-          else        tma2_load_4d(sa, &tmA, lbar, q * 64, w0 + kwi, h0 + khi, img);
+      Item it;
+      if (!work(i, it)) break;
+      const uint32_t bh_cur = static_cast<uint32_t>(it.bn / 2) * 128u;
+      const CUtensorMap* mapA = it.kind == 0 ? &tmA : (it.kind <= 2 ? &tmTB : &tmLR);
+      const int nrow = it.n0 + rank * (it.bn / 2);
+      for (int khi = it.kh_lo; khi < it.kh_hi; ++khi)
+        for (int kwi = it.kw_lo; kwi < it.kw_hi; ++kwi)
+          for (int q = 0; q < p.cchunks; ++q) {
+            const int kb = (khi * p.kw + kwi) * p.cchunks + q;          // k-block of the packed filter
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
+            const uint32_t lbar = full_bar(stage) & kPeerMask;           // the LEADER's full barrier
+            if (elect_one_sync()) {
+              // the leader expects the bytes of all loads of the pair; the second CTA's loads only complete_tx there
+              if (leader) mbar_expect_tx(full_bar(stage), 2u * (it.a_bytes + bh_cur));
+              if (p.flat && !p.ring) tma2_load_4d(sa, mapA, lbar, q * 64, it.cw + khi * p.wp + kwi, 0, it.img);
+              else                   tma2_load_4d(sa, mapA, lbar, q * 64, it.cw + kwi, it.ch + khi, it.img);
+              // filter rows in 64-row boxes: this CTA's half of the n-tile is one (BN = 128) or two (BN = 256) of them
+              tma2_load_2d(sb, &tmB, lbar, kb * 64, nrow);
+              if (it.bn == 256) tma2_load_2d(sb + 8192, &tmB, lbar, kb * 64, nrow + 64);
+            }
+            __syncwarp();
+            if (++stage == S) { stage = 0; phase ^= 1u; }
           }
-          // filter rows in 64-row boxes: this CTA's half of the n-tile is one (BN = 128) or two (BN = 256) of them
-          const int nrow = n0 + static_cast<int>(rank) * (bn_cur / 2);
-          tma2_load_2d(sb, &tmB, lbar, kb * 64, nrow);
-          if (bn_cur == 256) tma2_load_2d(sb + 8192, &tmB, lbar, kb * 64, nrow + 64);
-        }
-        __syncwarp();
-        if (++stage == S) { stage = 0; phase ^= 1u; }
-        if (++q == p.cchunks) { q = 0; if (++kwi == p.kw) { kwi = 0; ++khi; } }
-      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {
       int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
       for (int i = 0;; ++i) {
-        int t, bn_cur, nsub;
-        if (!work(i, t, bn_cur, nsub)) break;
-        const uint32_t idesc = bn_cur == p.bn ? p.idesc : p.idesc_half;
+        Item it;
+        if (!work(i, it)) break;
+        const uint32_t idesc = it.bn == p.bn ? p.idesc : p.idesc_half;
+        const int nkb = (it.kh_hi - it.kh_lo) * (it.kw_hi - it.kw_lo) * p.cchunks;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.bn);
-        for (int kb = 0; kb < p.kblocks; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = base + stage * stage_bytes, sb = sa + kAStageBytes;
@@ -211,7 +305,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int row = quad * 32 + lane;
     const int row_bytes = p.bn * 2, cpr = row_bytes >> 4;
     uint8_t* stg = smem + (epi0 - base);
-    int* rowinfo = reinterpret_cast<int*>(stg + 128 * row_bytes);
+    long long* rowinfo = reinterpret_cast<long long*>(stg + 128 * row_bytes);
     float* red = reinterpret_cast<float*>(rowinfo + 128);
     auto swz = [&](int k, int r) { return (k & ~7) | ((k ^ r) & 7); };
     const int pairs = p.bn >> 1, groups = 256 / pairs, rpg = 128 / groups;
@@ -227,25 +321,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       run = 0.f;
     };
-    for (int t = tile_begin; t < tile_end; ++t) {
-      int m_tile, n0, img, h0, w0;
-      decode(t, m_tile, n0, img, h0, w0);
-      const bool tile_ok = m_tile < p.num_m_tiles;
-      if (p.stats && tile_ok && (img != run_img || n0 != run_n0)) { flush_stats(); run_img = img; run_n0 = n0; }
-      int h, w; bool valid;
-      if (p.flat) { const int f = w0 + row; h = f / p.wp; w = f - h * p.wp; valid = (h < p.ho) && (w < p.wo); }
-      else { const int hh = row / p.tw; h = h0 + hh; w = w0 + (row - hh * p.tw);
-             valid = (row < p.tw * p.th) && (h < p.ho) && (w < p.wo); }
-      valid = valid && tile_ok;
+    for (int i = 0;; ++i) {
+      Item it;
+      if (!work(i, it)) break;
+      const int n0 = it.n0;
+      if (p.stats && it.ok && (it.img != run_img || n0 != run_n0)) { flush_stats(); run_img = it.img; run_n0 = n0; }
+      size_t pix;
+      const bool valid = rowmap(it, row, pix);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      if (p.exp & 1) {                                   // timing experiment: no epilogue work at all
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(tempty_bar(as));
-        if (++as == 2) { as = 0; aphase ^= 1u; }
-        continue;
-      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.bn);
       uint8_t* srow = stg + row * row_bytes;
       if (n0 != cur_n0) { load_bias_tile(sb, p.bias, n0, p.bn, p.cout, lane); cur_n0 = n0; }
@@ -267,23 +351,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           *reinterpret_cast<uint4*>(srow + swz(c0 / 8 + j, row) * 16) = pk;
         }
       }
-      if (half == 0) rowinfo[row] = valid ? static_cast<int>((static_cast<size_t>(img) * p.ho + h) * p.wo + w) : -1;
+      if (half == 0) rowinfo[row] = valid ? static_cast<long long>(pix) : -1;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tempty_bar(as));
       if (++as == 2) { as = 0; aphase ^= 1u; }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (!(p.exp & 2))
       for (int idx = et; idx < 128 * cpr; idx += 256) {
         const int r2 = idx / cpr, k = idx - r2 * cpr;
-        const int pi = rowinfo[r2];
+        const long long pi = rowinfo[r2];
         const int col0 = n0 + k * 8;
         if (pi >= 0 && col0 < p.cout) {
           const uint4 val = *reinterpret_cast<const uint4*>(stg + r2 * row_bytes + swz(k, r2) * 16);
           *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out) + (static_cast<size_t>(pi) * p.out_c + col0) * 2) = val;
         }
       }
-      if (p.stats && !(p.exp & 4)) {
+      if (p.stats) {
         const int cp = et % pairs, g = et / pairs;
         float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
         for (int r2 = g * rpg; r2 < (g + 1) * rpg; ++r2) {
@@ -304,7 +387,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     if (p.stats) flush_stats();
   } else if (warp >= 4) {
-    // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
+    // ===================== direct epilogue (both CTAs, own 128 TMEM lanes) =====================
     const int quad = warp & 3, half = (warp - 4) >> 2;
     const int row = quad * 32 + lane;
     int as = 0; uint32_t aphase = 0;
@@ -329,27 +412,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     };
     for (int i = 0;; ++i) {
-      int t, bn_cur, nsub;
-      if (!work(i, t, bn_cur, nsub)) break;
-      int m_tile, n0, img, h0, w0;
-      decode(t, m_tile, n0, img, h0, w0);
-      n0 += nsub * 128;
-      const bool tile_ok = m_tile < p.num_m_tiles;
-      if (p.stats && tile_ok && (img != run_img || n0 != run_n0)) { flush_stats(); run_img = img; run_n0 = n0; }
-      int h, w; bool valid;
-      if (p.flat) { const int f = w0 + row; h = f / p.wp; w = f - h * p.wp; valid = (h < p.ho) && (w < p.wo); }
-      else { const int hh = row / p.tw; h = h0 + hh; w = w0 + (row - hh * p.tw);
-             valid = (row < p.tw * p.th) && (h < p.ho) && (w < p.wo); }
-      valid = valid && tile_ok;
-      const size_t pix = (static_cast<size_t>(img) * p.ho + h) * p.wo + w;
-      if (n0 != cur_n0) { load_bias_tile(sb, p.bias, n0, bn_cur, p.cout, lane); cur_n0 = n0; }
+      Item it;
+      if (!work(i, it)) break;
+      const int n0 = it.n0;
+      if (p.stats && it.ok && (it.img != run_img || n0 != run_n0)) { flush_stats(); run_img = it.img; run_n0 = n0; }
+      size_t pix;
+      const bool valid = rowmap(it, row, pix);
+      if (n0 != cur_n0) { load_bias_tile(sb, p.bias, n0, it.bn, p.cout, lane); cur_n0 = n0; }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * p.bn);
 #pragma unroll
       for (int ci = 0; ci < 8; ++ci) {
         const int c0 = ci * 32;
-        if (c0 >= bn_cur) break;
+        if (c0 >= it.bn) break;
         if ((ci & 1) != half) continue;
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
@@ -403,6 +479,18 @@ void pick_box2(int wo, int ho, int* tw, int* th) {
   *th = t;
 }
 
+// relative cost of a launch in "rounds of BN = 256 tiles": whole rounds + the tail (split into BN = 128 halves when
+// they fit); a BN = 128 tile costs ~0.69 of a BN = 256 one (its MMAs are bound by shared-memory operand reads)
+double rounds_cost(int tiles256, int max_pairs, bool bn256) {
+  if (bn256) {
+    const int np = tiles256 < max_pairs ? tiles256 : max_pairs;
+    const int full = tiles256 / np, rem = tiles256 % np;
+    return full + (rem == 0 ? 0.0 : (2 * rem <= np ? 0.69 : 1.0));
+  }
+  const int t = 2 * tiles256, np = t < max_pairs ? t : max_pairs;
+  return 0.69 * ((t + np - 1) / np);
+}
+
 }  // namespace
 
 bool vcg_conv2_supported(const vcg_conv_desc* d, int out_f32) {
@@ -416,13 +504,29 @@ bool vcg_conv2_supported(const vcg_conv_desc* d, int out_f32) {
 
 int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y, float* stats,
                      cudaStream_t stream) {
-  const int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
+  int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
+  const int sms = vcg_num_sms();
   Conv2Args a{};
-  a.n_img = d->n; a.ho = ho; a.wo = wo; a.wp = d->wp;
-  a.flat = d->flat ? 1 : 0; a.kw = d->kw;
+  // interior + ring data gradient: flat == 2 promises a zero halo of (kh - 1, kw - 1) around dY; 3 x 3 filters on maps
+  // whose interior tiles exactly (16 x 16, 32 x 32, 64 x 64), no statistics
+  static const bool no_ring = getenv("VCG_NO_RING") && getenv("VCG_NO_RING")[0] == '1';        // A/B timing switch
+  const int hi = ho - 2, wi = wo - 2;                       // interior = the forward layer's input map
+  a.ring = (!no_ring && d->flat == 2 && d->kh == 3 && d->kw == 3 && !(d->stats && stats) && (wi == 16 || wi == 32 || wi == 64) &&
+            hi >= 8 && hi <= 128 && 128 % hi == 0 && hi % (128 / wi) == 0) ? 1 : 0;
+  a.n_img = d->n; a.wp = d->wp;
+  a.flat = d->flat ? 1 : 0; a.kh = d->kh; a.kw = d->kw;
   a.cchunks = d->c / 64;
-  a.kblocks = d->kh * (d->kwc_pad / 64);
-  if (a.flat) {
+  const int kblocks = d->kh * (d->kwc_pad / 64);
+  if (a.ring) {
+    ho = hi; wo = wi;                                       // the kernel's (ho, wo) is the interior
+    a.tw = wi; a.th = 128 / wi; a.tiles_w = 1; a.tiles_h = hi / a.th;
+    a.a_tx_bytes = 128 * 128;
+    a.tn_tb = 128 / (wi + 2); a.tn_lr = 128 / hi;
+    a.tb_tx_bytes = static_cast<uint32_t>(a.tn_tb * (wi + 2)) * 128u;
+    a.lr_tx_bytes = static_cast<uint32_t>(a.tn_lr * hi) * 128u;
+    a.p_tb = ((d->n + a.tn_tb - 1) / a.tn_tb + 1) / 2;
+    a.p_lr = ((d->n + a.tn_lr - 1) / a.tn_lr + 1) / 2;
+  } else if (a.flat) {
     a.tw = 128; a.th = 1; a.tiles_h = 1;
     a.tiles_w = (ho * d->wp + 127) / 128;
     a.a_tx_bytes = 128 * 128;
@@ -432,25 +536,29 @@ int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const
     a.tiles_h = (ho + a.th - 1) / a.th;
     a.a_tx_bytes = static_cast<uint32_t>(a.tw * a.th) * 128u;
   }
+  a.ho = ho; a.wo = wo;
   a.num_m_tiles = d->n * a.tiles_w * a.tiles_h;
+  const int m_pairs = (a.num_m_tiles + 1) / 2;
   int bn = d->cout_pad % 256 == 0 ? 256 : 128;
-  if (bn == 256 && static_cast<long long>((a.num_m_tiles + 1) / 2) * (d->cout_pad / 256) < vcg_num_sms() / 2) bn = 128;
+  if (bn == 256) {
+    const int t256 = m_pairs * (d->cout_pad / 256);
+    if (rounds_cost(t256, sms / 2, false) < rounds_cost(t256, sms / 2, true)) bn = 128;
+  }
   a.bn = bn;
   const int ntn = d->cout_pad / bn;
-  a.num_pair_tiles = ((a.num_m_tiles + 1) / 2) * ntn;
+  a.num_pair_tiles = m_pairs * ntn;
+  a.ring_pairs = a.ring ? (2 * a.p_tb + 2 * a.p_lr) * ntn : 0;
   a.cout = d->cout; a.out_c = d->out_c; a.act = d->act; a.stats = (d->stats && stats) ? 1 : 0;
   a.bias = bias; a.stats_acc = stats; a.out = y;
   a.idesc = umma_idesc_bf16(256, bn, 0, 0);
   a.idesc_half = umma_idesc_bf16(256, 128, 0, 0);
-  { static const int ex = getenv("VCG_EXP_EPI") ? atoi(getenv("VCG_EXP_EPI")) : 0; a.exp = ex; }
-  { static const bool sk = getenv("VCG_EXP_SKIPA") && getenv("VCG_EXP_SKIPA")[0] == '1'; a.skipa = sk ? 1 : 0; }
   static const bool no_epi2 = getenv("VCG_NO_EPI2") && getenv("VCG_NO_EPI2")[0] == '1';      // A/B timing switch
-  a.epi2 = (!no_epi2 && bn == 128 && static_cast<long long>(d->n) * ho * wo < (1LL << 31)) ? 1 : 0;
-  const int epi_bytes = a.epi2 ? 128 * bn * 2 + 512 + 4096 : 0;
+  a.epi2 = (!no_epi2 && bn == 128) ? 1 : 0;
+  const int epi_bytes = a.epi2 ? 128 * bn * 2 + 1024 + 4096 : 0;
   const int stage_bytes = kAStageBytes + (bn / 2) * 128;
   int stages = (227 * 1024 - 3072 - 8192 - epi_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
-  if (stages > a.kblocks) stages = a.kblocks;
+  if (stages > kblocks) stages = kblocks;
   a.stages = stages;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + 3072 + 8192 + epi_bytes;
 
@@ -460,7 +568,7 @@ int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const
   uint64_t dims[4], strides[3];
   uint32_t box[4];
   dims[0] = d->c;
-  if (a.flat) {
+  if (a.flat && !a.ring) {
     dims[1] = static_cast<uint64_t>(d->hp) * d->wp; dims[2] = 1; dims[3] = d->n;
     strides[0] = pix_stride; strides[1] = img_stride; strides[2] = img_stride;
     box[0] = 64; box[1] = 128; box[2] = 1; box[3] = 1;
@@ -471,6 +579,15 @@ int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const
   }
   int rc = vcg_encode_tmap(&tmA, x, 4, dims, strides, box, "conv_tc2 A");
   if (rc) return rc;
+  CUtensorMap tmTB = tmA, tmLR = tmA;
+  if (a.ring) {
+    uint32_t btb[4] = {64, static_cast<uint32_t>(wi + 2), 1, static_cast<uint32_t>(a.tn_tb)};
+    rc = vcg_encode_tmap(&tmTB, x, 4, dims, strides, btb, "conv_tc2 A (ring rows)");
+    if (rc) return rc;
+    uint32_t blr[4] = {64, 1, static_cast<uint32_t>(hi), static_cast<uint32_t>(a.tn_lr)};
+    rc = vcg_encode_tmap(&tmLR, x, 4, dims, strides, blr, "conv_tc2 A (ring columns)");
+    if (rc) return rc;
+  }
   const uint64_t ktot = static_cast<uint64_t>(d->kh) * d->kwc_pad;
   uint64_t bdims[2] = {ktot, static_cast<uint64_t>(d->cout_pad)};
   uint64_t bstr[1] = {ktot * es};
@@ -483,17 +600,15 @@ int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const
     VCG_REQUIRE(e == cudaSuccess, VCG_E_CUDA, "conv_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int sms = vcg_num_sms();
   int grid = (sms / 2) * 2;
   if (grid > 2 * a.num_pair_tiles) grid = 2 * a.num_pair_tiles;
-  {
-    // wave quantisation (1024-channel layers at 16 x 16: 256 tiles on 74 pairs = 3.46 rounds): run the whole rounds as
-    // BN = 256 tiles and cut the left-over tiles into two BN = 128 halves, so the last round costs half a tile
+  if (!a.ring) {
+    // wave quantisation: run the whole rounds as BN = 256 tiles and cut the left-over tiles into two BN = 128 halves
     static const bool no_tail = getenv("VCG_NO_TAIL") && getenv("VCG_NO_TAIL")[0] == '1';      // A/B timing switch
     const int npairs = grid / 2, full = a.num_pair_tiles / npairs, rem = a.num_pair_tiles % npairs;
     if (!no_tail && bn == 256 && full >= 1 && rem > 0 && 2 * rem <= npairs) { a.tail_r = rem; a.full_per_pair = full; }
   }
-  conv_tc2_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, a);
+  conv_tc2_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmTB, tmLR, a);
   VCG_CHECK_LAUNCH("conv_tc2_kernel");
   return VCG_OK;
 }

@@ -241,7 +241,7 @@ def conv_dgrad(spec: ConvSpec, dy_pad, w_dgrad, dxp):
     d_cout = spec.ci if (spec.wmap == L.WMAP_PLAIN and spec.ci < spec.cin_phys) else spec.cin_phys
     d = L.ConvDesc(dtype=L.dtype_code(dy_pad.dtype), n=n, hp=hd, wp=wd, c=c, kh=spec.pkh, kw=spec.pkw,
                    kwc_pad=spec.d_kwc_pad, cout=d_cout, cout_pad=spec.d_rows_pad, out_c=dxp.shape[-1],
-                   act=L.ACT_NONE, stats=0, flat=1, out_f32=0)
+                   act=L.ACT_NONE, stats=0, flat=2, out_f32=0)   # 2: dy_pad's outer (k-1) border is zero
     assert tuple(dxp.shape[:3]) == (n, hd - spec.pkh + 1, wd - spec.pkw + 1), (dxp.shape, dy_pad.shape)
     thin = _thin_kernel(dy_pad.dtype, c, d_cout, spec.d_rows_pad, spec.pkh, spec.pkw, wd - spec.pkw + 1, False)
     tok = _rec(f"conv_{thin}_dgrad" if thin else "conv_dgrad", spec.flops(n, hd - 2 * (spec.pkh - 1), wd - 2 * (spec.pkw - 1)),
