@@ -817,16 +817,9 @@ xform_bwd_norm_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y,
   const int p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
   const int wpd = p.w + 2 * p.dy_halo, hpd = p.h + 2 * p.dy_halo;
   float mean[8], rstd[8], m1[8], m2[8], s[8];
-  {
-    load_scale_shift(mr + (static_cast<size_t>(n) * p.c + ch) * 2, rstd, mean, p.stats_hw);
-    const float* gs = gsums_in + (static_cast<size_t>(n) * p.c + ch) * 2;
-    const float inv = 1.f / hw;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { m1[j] = gs[2 * j] * inv; m2[j] = gs[2 * j + 1] * inv; s[j] = 0.f; }
-  }
-  for (int pp = p0 + pl; pp < p1; pp += kXbU * lanes) {
-    Raw8<T> gr[kXbU], yr[kXbU];
-    T* dp[kXbU];
+  Raw8<T> gr[kXbU], yr[kXbU];
+  T* dp[kXbU];
+  auto issue = [&](int pp) {
 #pragma unroll
     for (int u = 0; u < kXbU; ++u) {
       const int q = min(pp + u * lanes, p1 - 1);
@@ -835,6 +828,24 @@ xform_bwd_norm_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y,
       ldraw(dp[u], gr[u]);
       ldraw(y + (static_cast<size_t>(n) * hw + q) * p.y_c + ch, yr[u]);
     }
+  };
+  // the first batch of data loads goes out BEFORE the per-channel statistics are fetched: small planes run only a
+  // few iterations per block, and the dependent statistics -> data round trips were a quarter of the kernel time
+  int pp = p0 + pl;
+  if (pp < p1) issue(pp);
+  {
+    load_scale_shift(mr + (static_cast<size_t>(n) * p.c + ch) * 2, rstd, mean, p.stats_hw);
+    const float* gs = gsums_in + (static_cast<size_t>(n) * p.c + ch) * 2;
+    const float inv = 1.f / hw;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                           // 16-byte loads (scalar ones cost 8x the L2 sectors)
+      const float4 t = *reinterpret_cast<const float4*>(gs + 4 * q);
+      m1[2 * q] = t.x * inv; m2[2 * q] = t.y * inv; m1[2 * q + 1] = t.z * inv; m2[2 * q + 1] = t.w * inv;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  }
+  while (pp < p1) {
 #pragma unroll
     for (int u = 0; u < kXbU; ++u) {
       if (pp + u * lanes >= p1) break;
@@ -849,6 +860,8 @@ xform_bwd_norm_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y,
       }
       st8<T>(dp[u], g);
     }
+    pp += kXbU * lanes;
+    if (pp < p1) issue(pp);
   }
   if (dbias)
     reduce_groups<8>(s, cgl, sred, [&](int l, int j, float t) { atomicAdd(dbias + (blockIdx.z * 32 + l) * 8 + j, t); });
@@ -932,10 +945,16 @@ static int pix_chunk(int hw, int n, int zc) {
 }
 
 // fast backward kernels: ~8 blocks per SM in flight over the whole launch, whole unrolled iterations per thread
-static int pix_chunk_fast(int hw, int n, int zc, int cg_total) {
+// pixels per block of the backward fast paths.  Every block pays a fixed prologue (per-channel statistics) and
+// epilogue (bias-gradient reduction + atomics), so small planes want FEWER, longer blocks; large planes want
+// several waves for load balance.  mult = blocks per SM aimed for (measured on B200, tools/bench_xform.py:
+// InstanceNorm backward 1024ch 16x16: 55 us at 8, 37 us at 2; 64ch 256x256: 291 us at 8, 376 us at 2).
+static int pix_chunk_fast(int hw, int n, int zc, int cg_total, int mult) {
+  static const int force = getenv("VCG_XF_WAVES") ? atoi(getenv("VCG_XF_WAVES")) : 0;      // A/B timing switch
+  if (force > 0) mult = force;
   const int cgl = cg_total < 32 ? cg_total : 32;
   const int step = kXbUmax * (256 / cgl);                  // pixels one block covers per unrolled iteration
-  long long want = 8LL * vcg_num_sms();
+  long long want = static_cast<long long>(mult) * vcg_num_sms();
   long long per = (static_cast<long long>(hw) * n * zc + want - 1) / want;
   if (per < 2 * step) per = 2 * step;
   per = (per + step - 1) / step * step;
@@ -1092,7 +1111,7 @@ extern "C" int vcg_xform_bwd_gather(const vcg_xbwd_desc* d, const vcg_gsrc* srcs
       VCG_REQUIRE(f.img_stride < (1LL << 31), VCG_E_UNSUPPORTED, "xform_bwd_gather: image too large for 32-bit offsets");
       f.base = static_cast<const char*>(srcs[k].dxp) + first * es;
     }
-    const int ppb = pix_chunk_fast(hw, d->n, zc, cg_total);
+    const int ppb = pix_chunk_fast(hw, d->n, zc, cg_total, hw <= 1024 ? 4 : 8);
     dim3 grid((hw + ppb - 1) / ppb, d->n, zc);
     // 4 pixels per thread per iteration at 2 blocks/SM measured best on B200 (4.2 TB/s; 2 px x 3 blocks: 3.7)
     if (d->dtype == VCG_F32)
@@ -1172,7 +1191,7 @@ extern "C" int vcg_xform_bwd_norm(const vcg_xbwd_desc* d, const void* y, const f
   const int zc = (d->c / 8 + 31) / 32, hw = d->h * d->w;
   const int cg_total = d->c / 8;
   if ((cg_total & (cg_total - 1)) == 0 && (reinterpret_cast<uintptr_t>(mean_rstd) & 15) == 0) {
-    const int ppb = pix_chunk_fast(hw, d->n, zc, cg_total);
+    const int ppb = pix_chunk_fast(hw, d->n, zc, cg_total, hw >= 16384 ? 8 : (hw >= 4096 ? 4 : 2));
     dim3 grid((hw + ppb - 1) / ppb, d->n, zc);
     if (d->dtype == VCG_F32)
       xform_bwd_norm_kernel<float><<<grid, 256, 0, stream>>>(a, static_cast<const float*>(y), mean_rstd, gsums,
