@@ -90,6 +90,9 @@ __device__ __forceinline__ float act_grad(float o, int act) {
   if (act == VCG_ACT_LEAKY) return o > 0.f ? 1.f : 0.2f;
   return 1.f;
 }
+// branch-free form for inner loops: slope = act_slope(act) once per kernel, then one compare + select per element
+__device__ __forceinline__ float act_slope(int act) { return act == VCG_ACT_RELU ? 0.f : (act == VCG_ACT_LEAKY ? 0.2f : 1.f); }
+__device__ __forceinline__ float act_grad_s(float o, float slope) { return o > 0.f ? 1.f : slope; }
 // PyTorch 'reflect' index (edge not repeated) for t in [-p, L-1+p], p < L
 __device__ __forceinline__ int reflect_idx(int t, int L) {
   t = t < 0 ? -t : t;

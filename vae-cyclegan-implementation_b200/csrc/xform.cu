@@ -716,6 +716,7 @@ xform_bwd_gather_kernel(const __grid_constant__ XgArgs p, const T* __restrict__ 
   if (p.norm) load_scale_shift(mr + (static_cast<size_t>(n) * p.c + ch) * 2, sc, sf, p.stats_hw);
   if (p.clear_halo && p.dy_halo > 0) clear_halo_share<T>(dy, n, p.h, p.w, p.dy_halo, p.dy_c, ch, blockIdx.x * lanes + pl, gridDim.x * lanes);
   const bool need_y = p.norm || p.act || p.pre_act;
+  const float slope_act = act_slope(p.act), slope_pre = act_slope(p.pre_act);
   for (int pp = p0 + pl; pp < p1; pp += kXbU * lanes) {
     int hh[kXbU], ww[kXbU];
     float g[kXbU][8];
@@ -772,14 +773,14 @@ xform_bwd_gather_kernel(const __grid_constant__ XgArgs p, const T* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = (yv[j] - sf[j]) * sc[j];
-          g[u][j] *= act_grad(z, p.act);
+          g[u][j] *= act_grad_s(z, slope_act);
           s[j] += g[u][j]; s[8 + j] = fmaf(g[u][j], z, s[8 + j]);
         }
       } else if (need_y) {
         // no norm: at most one activation (fused in the conv epilogue or applied after): y or act(y) share sign
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          g[u][j] *= act_grad(yv[j], p.act) * act_grad(yv[j], p.pre_act);
+          g[u][j] *= act_grad_s(yv[j], slope_act) * act_grad_s(yv[j], slope_pre);
           s[j] += g[u][j];
         }
       } else {
@@ -817,6 +818,7 @@ xform_bwd_norm_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y,
   const int p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
   const int wpd = p.w + 2 * p.dy_halo, hpd = p.h + 2 * p.dy_halo;
   float mean[8], rstd[8], m1[8], m2[8], s[8];
+  const float slope_pre = act_slope(p.pre_act);
   Raw8<T> gr[kXbU], yr[kXbU];
   T* dp[kXbU];
   auto issue = [&](int pp) {
@@ -855,7 +857,7 @@ xform_bwd_norm_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y,
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float z = (yv[j] - mean[j]) * rstd[j];
-        g[j] = rstd[j] * (g[j] - m1[j] - z * m2[j]) * act_grad(yv[j], p.pre_act);
+        g[j] = rstd[j] * (g[j] - m1[j] - z * m2[j]) * act_grad_s(yv[j], slope_pre);
         s[j] += g[j];
       }
       st8<T>(dp[u], g);
