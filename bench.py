@@ -267,7 +267,7 @@ def run_ours(args):
     if os.path.exists(tpath):     # ncu --set full capture of one representative launch (committed evidence)
         tj = json.load(open(tpath))
         traffic, traffic_of = tj.get("conv_tc_kernel_dram_bytes_per_launch"), tj.get("launch")
-    roofline = {"kernel": "conv_tc_kernel (tcgen05 implicit GEMM: forward + data-gradient launches)",
+    roofline = {"kernel": "conv_tc2_kernel / conv_tc_kernel (tcgen05 implicit GEMM, CTA-pair and single-CTA: forward + data-gradient launches)",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_of": traffic_of, "peak_source": pk["source"],
                 "launches_per_step": tc_n / max(1, args.steps), "share_of_step": tc_ms / ms,
