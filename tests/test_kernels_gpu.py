@@ -125,6 +125,8 @@ CONV_CASES = [  # (name, n, H, W, ci_in, co, k, wmap)
     ("tailsplit", 80, 16, 16, 64, 256, 3, 0),
     # data gradient as interior tiles + border-ring tiles that batch images (partial image groups, odd group counts)
     ("ring16", 9, 16, 16, 128, 128, 3, 0), ("ring16wide", 23, 16, 16, 256, 256, 3, 0), ("ring32", 5, 32, 32, 128, 256, 3, 0), ("ring64", 3, 64, 64, 128, 128, 3, 0),
+    # 256-channel-multiple outputs: CTA-pair weight-gradient kernel (K split over pixel blocks)
+    ("wgpair", 2, 32, 32, 256, 512, 3, 0),
 ]
 
 

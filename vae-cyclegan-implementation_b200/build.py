@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvcg_b200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["abi.cu", "conv_tc.cu", "conv_tc_fold.cu", "conv_tc2.cu", "wgrad_tc.cu", "wgrad_fold.cu", "conv_simt.cu", "wgrad_thin.cu", "xform.cu", "wpack.cu", "losses.cu", "adam.cu"]
+SOURCES = ["abi.cu", "conv_tc.cu", "conv_tc_fold.cu", "conv_tc2.cu", "wgrad_tc.cu", "wgrad_tc2.cu", "wgrad_fold.cu", "conv_simt.cu", "wgrad_thin.cu", "xform.cu", "wpack.cu", "losses.cu", "adam.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

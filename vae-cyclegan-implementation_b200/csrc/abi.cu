@@ -84,6 +84,8 @@ extern "C" int vcg_probe_tmap(const void* base, int32_t rank, const uint64_t* di
 // ---------------------------------------------------------------- convolution dispatch
 int vcg_conv_fwd_tc(const vcg_conv_desc*, const void*, const void*, const float*, void*, float*, int, cudaStream_t);
 int vcg_conv_wgrad_tc(const vcg_conv_desc*, const void*, const void*, int, int, float*, cudaStream_t);
+bool vcg_wgrad2_supported(const vcg_conv_desc*, int);
+int vcg_conv_wgrad_tc2(const vcg_conv_desc*, const void*, const void*, int, int, float*, cudaStream_t);
 int vcg_conv_fwd_simt(const vcg_conv_desc*, int, const void*, const void*, const float*, void*, int, cudaStream_t);
 int vcg_conv_wgrad_simt(const vcg_conv_desc*, int, const void*, const void*, int, int, float*, cudaStream_t);
 int vcg_conv_wgrad_thin(const vcg_conv_desc*, const void*, const void*, int, int, float*, cudaStream_t);
@@ -126,5 +128,7 @@ extern "C" int vcg_conv_wgrad(const vcg_conv_desc* d, const void* x, const void*
   if (d->dtype == VCG_BF16 && !force_simt() && vcg_wgrad_thin_supported(d)) return vcg_conv_wgrad_thin(d, x, dy, dy_halo, dy_c, dw, stream);
   if (d->dtype == VCG_F32 || force_simt() || d->cout < 16 || !tileable)
     return vcg_conv_wgrad_simt(d, d->dtype, x, dy, dy_halo, dy_c, dw, stream);
+  // 256-channel-multiple outputs: CTA-pair kernel (256 x 256 tiles, half of the X tile per CTA)
+  if (vcg_wgrad2_supported(d, dy_c)) return vcg_conv_wgrad_tc2(d, x, dy, dy_halo, dy_c, dw, stream);
   return vcg_conv_wgrad_tc(d, x, dy, dy_halo, dy_c, dw, stream);
 }
