@@ -74,6 +74,6 @@ def test_sass_is_blackwell_native(vcg):
             fn = line.split("Function :")[1].strip()
         elif " HMMA" in line:
             assert fn is not None and "wgrad_thin" in fn, f"legacy HMMA in {fn}"
-    for must in ("conv_tc_kernel", "wgrad_tc_kernel", "conv_tc_fold_kernel", "wgrad_fold_kernel"):
+    for must in ("conv_tc_kernel", "conv_tc2_kernel", "wgrad_tc_kernel", "wgrad_tc2_kernel", "conv_tc_fold_kernel", "wgrad_fold_kernel"):
         body = sass.split(must, 1)[1].split("Function :", 1)[0] if must in sass else ""
         assert "UTCHMMA" in body, must
