@@ -4,8 +4,8 @@ timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q --tb=short -k "conv
 echo "tests rc=$?" >> gpurun_out/wtc2_tests.log
 tail -12 gpurun_out/wtc2_tests.log | cut -c1-200
 if grep -q "tests rc=0" gpurun_out/wtc2_tests.log; then
-  L="eR_b64 eD4 eD3 eD2 dU1_b64 dU2_b64"
-  VCG_WTC2=0 timeout 300 python tools/bench_conv.py $L > gpurun_out/wtc2_off.jsonl 2>&1
+  L="dU4_b64 p_k3"
+  VCG_NO_WSWAP=1 timeout 300 python tools/bench_conv.py $L > gpurun_out/wtc2_off.jsonl 2>&1
   timeout 300 python tools/bench_conv.py $L > gpurun_out/wtc2_on.jsonl 2>&1
   paste -d'\n' gpurun_out/wtc2_off.jsonl gpurun_out/wtc2_on.jsonl | python -c "
 import sys,json
