@@ -127,6 +127,8 @@ CONV_CASES = [  # (name, n, H, W, ci_in, co, k, wmap)
     ("ring16", 9, 16, 16, 128, 128, 3, 0), ("ring16wide", 23, 16, 16, 256, 256, 3, 0), ("ring32", 5, 32, 32, 128, 256, 3, 0), ("ring64", 3, 64, 64, 128, 128, 3, 0),
     # 256-channel-multiple outputs: CTA-pair weight-gradient kernel (K split over pixel blocks)
     ("wgpair", 2, 32, 32, 256, 512, 3, 0),
+    # data gradient with 64 output channels on the CTA-pair kernel (flat tiling at 128 x 128)
+    ("n64flat", 1, 128, 128, 64, 128, 3, 0),
 ]
 
 

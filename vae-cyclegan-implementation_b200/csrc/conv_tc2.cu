@@ -497,7 +497,10 @@ bool vcg_conv2_supported(const vcg_conv_desc* d, int out_f32) {
   static const bool off = getenv("VCG_TC2") && getenv("VCG_TC2")[0] == '0';        // A/B timing switch
   if (off || out_f32) return false;
   if (d->c % 64 != 0 || d->kwc_pad != d->kw * d->c) return false;
-  if (d->cout_pad % 128 != 0 || d->cout != d->cout_pad || d->out_c != d->cout) return false;
+  // 128-channel-multiple outputs; 64 output channels only for data gradients (no statistics: the thin-N epilogue of
+  // conv_tc.cu is the better forward path at N = 64)
+  const bool n64 = d->cout_pad == 64 && d->flat != 0 && !d->stats;
+  if ((d->cout_pad % 128 != 0 && !n64) || d->cout != d->cout_pad || d->out_c != d->cout) return false;
   const int kblocks = d->kh * (d->kwc_pad / 64);
   return kblocks >= 8;
 }
@@ -539,7 +542,7 @@ int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const
   a.ho = ho; a.wo = wo;
   a.num_m_tiles = d->n * a.tiles_w * a.tiles_h;
   const int m_pairs = (a.num_m_tiles + 1) / 2;
-  int bn = d->cout_pad % 256 == 0 ? 256 : 128;
+  int bn = d->cout_pad % 256 == 0 ? 256 : (d->cout_pad == 64 ? 64 : 128);
   if (bn == 256) {
     const int t256 = m_pairs * (d->cout_pad / 256);
     if (rounds_cost(t256, sms / 2, false) < rounds_cost(t256, sms / 2, true)) bn = 128;
@@ -591,7 +594,7 @@ int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const
   const uint64_t ktot = static_cast<uint64_t>(d->kh) * d->kwc_pad;
   uint64_t bdims[2] = {ktot, static_cast<uint64_t>(d->cout_pad)};
   uint64_t bstr[1] = {ktot * es};
-  uint32_t bbox[2] = {64, 64};                              // 64 filter rows per box: one (BN = 128) or two (BN = 256) per CTA and stage
+  uint32_t bbox[2] = {64, bn == 64 ? 32u : 64u};            // filter rows per box: this CTA's half at BN <= 128, two boxes at BN = 256
   rc = vcg_encode_tmap(&tmB, w, 2, bdims, bstr, bbox, "conv_tc2 B");
   if (rc) return rc;
   static bool attr_set = false;
