@@ -280,6 +280,62 @@ def test_state_dict_round_trip_and_optimizer_state(env):
 
 
 # ------------------------------------------------------------------------------------------------
+def test_graph_replay_matches_eager_steps(env):
+    """vcg_b200.graph.GraphedStep (what bench.py times).  Two CUDA-graph replayed steps, the second fed from a pinned
+    host batch: (a) prefetched on the side stream during the first replay, (b) copied at call time -- both protocols
+    must give the same metrics and weights (fp32 mode: only the atomics' summation order differs); and the replayed
+    step must agree with the eager step on the same data (different noise draw: compared on the cycle loss)."""
+    N, plan, rp = env
+    from vcg_b200.graph import GraphedStep
+    plan.set_precision("fp32")
+    b0 = rp.synthetic_batch(1)
+    g = torch.Generator().manual_seed(99)
+    b1 = {"x": torch.rand(1, 3, 256, 256, generator=g), "y": torch.rand(1, 3, 256, 256, generator=g)}
+    host1 = {k: v.pin_memory() for k, v in b1.items()}
+
+    def fresh():
+        torch.manual_seed(5)
+        m = N.CycleVAEGAN(paired=False).cuda()
+        m.configure_optimizers(lr=2e-4)
+        m.configure_loss(**rp.DEFAULT_LAMBDAS)
+        m.train()
+        return m
+
+    eager = fresh()
+    e0 = eager.training_step({k: v.cuda() for k, v in b0.items()})
+    e1 = eager.training_step({k: v.cuda() for k, v in b1.items()})
+
+    def run(prefetch):
+        m = fresh()
+        torch.manual_seed(77)
+        r = GraphedStep(m, {k: v.cuda() for k, v in b0.items()}, warmup=1)
+        torch.manual_seed(78)
+        a = r({k: v.cuda() for k, v in b0.items()}, prefetch=host1 if prefetch else None)
+        b = r(host1)
+        return a, b, m
+
+    a_p, b_p, m_p = run(True)
+    a_d, b_d, m_d = run(False)
+    for k in a_d:
+        disc = "gan" in k or k.startswith(("D_loss", "d_"))
+        tol = 5e-2 if disc else 1e-3
+        assert abs(a_p[k] - a_d[k]) <= tol * max(1.0, abs(a_d[k])), (k, a_p[k], a_d[k])
+        assert abs(b_p[k] - b_d[k]) <= tol * max(1.0, abs(b_d[k])), (k, b_p[k], b_d[k])
+    # the replayed steps really trained, identically under both protocols
+    key = "G.encoder.model.1.conv.weight"
+    w_p, w_d, w_0 = m_p.state_dict()[key], m_d.state_dict()[key], fresh().state_dict()[key]
+    # (Adam's first steps move every weight by ~lr * sign(g): a near-zero gradient whose sign depends on the atomics'
+    # summation order moves by a full +-lr, so the protocols agree to a fraction of the update, not to 1e-5)
+    moved = rel_l2(w_d, w_0)
+    assert moved > 1e-4
+    assert rel_l2(w_p, w_d) < 0.3 * moved
+    # replay vs eager on the same data (the noise draws differ): cycle loss within a few percent
+    assert abs(a_d["loss_cycle"] - e0["loss_cycle"]) <= 5e-2 * abs(e0["loss_cycle"])
+    assert abs(b_d["loss_cycle"] - e1["loss_cycle"]) <= 5e-2 * abs(e1["loss_cycle"])
+    plan.set_precision("bf16")
+
+
+# ------------------------------------------------------------------------------------------------
 def test_validation_step_and_eval_mode(env):
     """validation_step in eval() mode (stale spectral-norm sigma) against the oracle."""
     N, plan, rp = env
