@@ -66,6 +66,9 @@ def build_parser():
     p.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
     p.add_argument("--seed", type=int, default=1234)
     p.add_argument("--output_dir", type=str, default="runs")
+    p.add_argument("--cuda_graph", action="store_true",
+                   help="replay training_step as one CUDA graph (fixed batch shape) and prefetch the next pinned "
+                        "host batch on a side stream during the step (vcg_b200.graph.GraphedStep)")
     p.add_argument("--no_cuda", action="store_true", help="accepted for compatibility; there is no CPU path")
     return p
 
@@ -93,9 +96,23 @@ def train_epoch(model, dataloader, device, args=None):
     """The reference's epoch loop around the hot path (train.py:80-128): H2D copy, training_step, metric sums."""
     model.train()
     sums, n = {}, 0
-    for batch in dataloader:
-        batch = {"x": batch["x"].to(device, non_blocking=True), "y": batch["y"].to(device, non_blocking=True)}
-        metrics = model.training_step(batch)
+    use_graph = bool(getattr(args, "cuda_graph", False))
+    it = iter(dataloader)
+    nxt = next(it, None)
+    while nxt is not None:
+        batch, nxt = nxt, next(it, None)
+        if use_graph:
+            # one graph per model (fixed batch shape); the look-ahead batch is copied during the replay
+            runner = getattr(model, "_vcg_graphed_step", None)
+            if runner is None:
+                from .graph import GraphedStep
+                dev_batch = {"x": batch["x"].to(device), "y": batch["y"].to(device)}
+                runner = model._vcg_graphed_step = GraphedStep(model, dev_batch, warmup=2)
+            same_shape = nxt is not None and nxt["x"].shape == batch["x"].shape and nxt["x"].is_pinned()
+            metrics = runner(batch, prefetch=nxt if same_shape else None)
+        else:
+            batch = {"x": batch["x"].to(device, non_blocking=True), "y": batch["y"].to(device, non_blocking=True)}
+            metrics = model.training_step(batch)
         if "G_loss" not in metrics:
             raise KeyError("training_step must report 'G_loss' (train.py:100-104)")
         for k, v in metrics.items():
