@@ -490,6 +490,7 @@ class _PairedGAN(_Composite):
     def configure_optimizers(self, lr=2e-4, betas=(0.5, 0.999)):
         self.optimizer_G = self._adam(self.G.parameters(), lr, betas)
         self.optimizer_D = self._adam(self.D.parameters(), lr, betas)
+        self.optimizer_G.overlap = True      # Adam(G) runs beside the discriminator backward (joined in _items)
         return self.optimizer_G, self.optimizer_D
 
     def _require(self):
@@ -781,6 +782,7 @@ class CycleAEGAN(_Cycle):
     def configure_optimizers(self, lr=1e-4, betas=(0.5, 0.999)):
         self.optimizer_G = self._adam(list(self.F.parameters()) + list(self.G.parameters()), lr, betas)
         self.optimizer_D = self._adam(list(self.DX.parameters()) + list(self.DY.parameters()), lr, betas)
+        self.optimizer_G.overlap = True      # Adam(F+G) runs beside the discriminator backward (joined in _items)
         return self.optimizer_G, self.optimizer_D
 
     def configure_loss(self, **kwargs):

@@ -38,6 +38,10 @@ class FusedAdam(torch.optim.Adam):
         self.defer = False          # dist.py: step() only starts the all-reduce; finish() joins it and updates, so
                                     # that the exchange overlaps whatever the caller runs in between
         self._deferred = False
+        self.overlap = False        # single-process two-optimiser models: step() launches the Adam kernel on a side
+                                    # stream so that it overlaps the discriminator backward; finish() joins it
+        self._side = None
+        self._side_pending = False
 
     # ---- flat gradient buffer -------------------------------------------------------------
     def _params(self):
@@ -92,12 +96,24 @@ class FusedAdam(torch.optim.Adam):
         if self.defer:
             self._deferred = True
             return loss
+        ps = self._params()
+        if self.overlap and self.pre_step_hook is None and ps and ps[0].is_cuda:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=ps[0].device)
+            self._side.wait_stream(torch.cuda.current_stream(ps[0].device))
+            with torch.cuda.stream(self._side):
+                self._update()
+            self._side_pending = True
+            return loss
         self._update()
         return loss
 
     @torch.no_grad()
     def finish(self):
         """Complete a deferred step (join the gradient exchange, run the Adam kernel)."""
+        if self._side_pending:
+            self._side_pending = False
+            torch.cuda.current_stream(self._params()[0].device).wait_stream(self._side)
         if self._deferred:
             self._deferred = False
             self._update()
