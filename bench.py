@@ -223,6 +223,11 @@ def run_ours(args):
     ms = timed(step_resident, args.steps)
     records = ops.prof_end() if not args.graph else []
     launches = lib.launch_count() - n0
+    # ---- end-to-end through the public API with host buffers (right after the resident measurement, same clocks)
+    if args.graph:
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
     if args.graph:
         # kernels inside a replayed graph are not re-issued by the library, so they are neither counted nor
         # event-timed there: run the same steps once more eagerly (after the timed region) to count the
@@ -232,12 +237,12 @@ def run_ours(args):
         ms_eager = timed(lambda: model.training_step({"x": x_dev, "y": y_dev}), args.steps)
         records = ops.prof_end()
         launches = lib.launch_count() - n0
+    if not args.graph:
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     value = args.global_batch * args.steps / (ms / 1e3)
-    # ---- end-to-end through the public API with host buffers
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
     e2e_value = args.global_batch * args.steps / (ms_e2e / 1e3)
     h2d = 2 * per * 3 * 256 * 256 * 4
     d2h = 4 * len(last)
