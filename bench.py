@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=2, help="bounded CPU sample: batch of the reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=1, help="1: independent passes of the step on two streams (vcg_b200.lanes)")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (vcg_b200.graph.GraphedStep)")
     return ap.parse_args()
 
@@ -156,6 +157,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     lib.load()
     plan.set_precision(args.precision)
+    from vcg_b200 import lanes
+    lanes.set_enabled(bool(args.lanes))
     if args.global_batch % world:
         raise SystemExit("global batch must be divisible by the number of GPUs")
     per = args.global_batch // world
@@ -293,7 +296,7 @@ def run_ours(args):
                                "256x256 training step, global batch %d, per-GPU batch %d" % (args.global_batch, per),
                    "global_batch": args.global_batch, "parallelism": f"dp{world}", "latent_dim": 64,
                    "l2": "working set (weights 276 MB bf16 + >10 GB activations per step) exceeds the 126 MB L2; no flush needed",
-                   "dead_passes_skipped": True, "cuda_graph": bool(args.graph),
+                   "dead_passes_skipped": True, "cuda_graph": bool(args.graph), "lanes": bool(args.lanes),
                    "roofline_timing": ("conv GEMM launches event-timed in an eager re-run of the same steps right after the "
                                        "graph-replayed timed region" if args.graph else "event-timed inside the timed region")},
         "roofline": roofline,

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VCG_ABI_VERSION 1
+#define VCG_ABI_VERSION 2
 #define VCG_API __attribute__((visibility("default")))
 
 enum { VCG_OK = 0, VCG_E_INVALID = -1, VCG_E_UNSUPPORTED = -2, VCG_E_CUDA = -3, VCG_E_DRIVER = -4 };
@@ -50,6 +50,11 @@ VCG_API int vcg_version(void);
 VCG_API const char* vcg_last_error(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
 VCG_API long long vcg_launch_count(void);
+/* Grid budget of the persistent tensor-core kernels (process-wide, read at launch time): at most `sms` CTAs per
+ * launch; 0 = every SM.  The host side runs two independent network passes (e.g. G(x) and F(y) of
+ * Networks.py:1909-1914) on two streams and gives each half of the machine, so that small-batch layers whose
+ * tile count cannot fill 148 SMs run side by side instead of one after the other.                              */
+VCG_API int vcg_set_sm_budget(int32_t sms);
 
 /* Multi-tensor variants: ONE launch packs (both layouts) or unpacks every filter of a network.
  * The caller fills d / pointers / accumulate for each job, runs vcg_wjob_plan on the HOST array (it assigns
@@ -238,8 +243,15 @@ typedef struct vcg_adam_chunk {  /* one <=65536-element slice of one tensor */
 } vcg_adam_chunk;
 /* state_dev: 4 device floats {step, lr/bias_corr1, sqrt(bias_corr2), -}: the step counter is advanced
  * and the bias corrections are recomputed ON THE DEVICE by each call (CUDA-graph replayable).          */
+enum { VCG_ADAM_TICK = 1,        /* advance the step counter / bias corrections (once per optimiser step) */
+       VCG_ADAM_GRAD_BF16 = 2,   /* chunk.g points to bfloat16 gradients (all-reduced wire buffer) */
+       VCG_ADAM_ZERO_GRAD = 4 }; /* zero the fp32 gradient after reading it (next zero_grad() is free) */
 VCG_API int vcg_adam_multi(const vcg_adam_chunk* chunks_dev, int32_t nchunks, float* state_dev, float lr,
-                           float beta1, float beta2, float eps, float grad_scale, void* stream);
+                           float beta1, float beta2, float eps, float grad_scale, int32_t flags, void* stream);
+/* dst(bf16)[i] = src(fp32)[i] (round to nearest even), optionally src[i] = 0: packs a slice of the flat gradient
+ * buffer into the bf16 wire buffer of the data-parallel all-reduce (the reference has no collective at all;
+ * this is the exchange step SURVEY.md 8e adds).                                                             */
+VCG_API int vcg_cast_bf16(float* src, void* dst, int64_t n, int32_t zero_src, void* stream);
 
 /* test hook: encode a bf16 SWIZZLE_128B tiled TMA descriptor only (no launch) */
 VCG_API int vcg_probe_tmap(const void* base, int32_t rank, const uint64_t* dims,

@@ -29,14 +29,15 @@ from oracle import ref_port as rp  # noqa: E402
 
 REF_CLASS = {"autoencoder": "Autoencoder", "vae": "VariationalAutoencoder", "aegan": "AEGAN",
              "vaegan": "VAEGAN", "cycleae": "CycleAE", "cyclevae": "CycleVAE",
-             "cycleaegan": "CycleAEGAN", "cyclevaegan": "CycleVAEGAN"}
+             "cycleaegan": "CycleAEGAN", "cyclevaegan": "CycleVAEGAN",
+             "doubleae": "DoubleAutoencoder", "doublevae": "DoubleVariationalAutoencoder"}
 
 
 def build_reference(arch, latent, paired):
     import Networks  # the reference module
     cls = getattr(Networks, REF_CLASS[arch])
     kw = {}
-    if arch in ("vae", "vaegan", "cyclevae", "cyclevaegan"):
+    if arch in ("vae", "vaegan", "cyclevae", "cyclevaegan", "doublevae"):
         kw["latent_dim"] = latent
     if arch.startswith("cycle"):
         kw["paired"] = paired
@@ -49,7 +50,7 @@ def checksum(state):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--archs", default=",".join(rp.ARCHS))
+    ap.add_argument("--archs", default=",".join(rp.ARCHS + rp.DOUBLE_ARCHS))
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--latent", type=int, default=64)

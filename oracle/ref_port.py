@@ -14,7 +14,14 @@ What it restates (all file:line relative to the reference checkout):
   * the eight composite training steps ... Networks.py:334-384 (Autoencoder),
     918-953 (VAE), 1068-1136 (AEGAN), 1254-1308 (VAEGAN), 1397-1439 (CycleAE),
     1525-1572 (CycleVAE), 1712-1807 (CycleAEGAN), 1973-2078 (CycleVAEGAN)
+  * the two shared-encoder pretraining models ... Networks.py:415-605 (DoubleAutoencoder),
+    608-852 (DoubleVariationalAutoencoder)
   * the constructor RNG order (nested ``apply(_init_weights)`` re-draws)
+
+``emulate_bf16()`` additionally restates WHERE the sm_100a kernels round to bfloat16 (conv operands and
+stored activations / gradients; accumulation, statistics, losses and Adam stay fp32), so that the
+tensor-core path can be held to a tight tolerance end to end instead of to the reference's own bf16
+noise: see the "bf16 emulation" section below.
 
 The arithmetic itself lives in a third-party dependency of the reference
 (``requirements.txt:1``: ``torch>=2.0.0``, unpinned; 2.11.0+cu128 in this image),
@@ -81,13 +88,14 @@ def vdb_convs(latent):
 
 ARCHS = ("autoencoder", "vae", "aegan", "vaegan", "cycleae", "cyclevae",
          "cycleaegan", "cyclevaegan")
+DOUBLE_ARCHS = ("doubleae", "doublevae")
 ALIASES = {"ae": "autoencoder", "vae_gan": "vaegan", "cycle_vae": "cyclevae",
            "vae_cyclegan": "cyclevaegan"}
 
 
 def canonical_arch(name):
     name = ALIASES.get(name, name)
-    if name not in ARCHS:
+    if name not in ARCHS and name not in DOUBLE_ARCHS:
         raise ValueError(f"unknown architecture {name!r}")
     return name
 
@@ -206,6 +214,23 @@ def init_state(arch, latent_dim=64, dtype=torch.float32):
         _build_discriminator(st, "DY.", dtype)
         for k in _ae_keys("F.") + _ae_keys("G.") + _disc_keys("DX.") + _disc_keys("DY."):
             _kaiming(st, k)
+    elif arch == "doubleae":                    # Networks.py:434-440 (no outer apply)
+        _build_convnet(st, "encoder.", ENCODER_CONVS, dtype)
+        _build_convnet(st, "decoder_A.", DECODER_CONVS, dtype)
+        _build_convnet(st, "decoder_B.", DECODER_CONVS, dtype)
+    elif arch == "doublevae":                   # Networks.py:626-645 (outer apply re-draws everything)
+        _build_convnet(st, "encoder.", ENCODER_CONVS, dtype)
+        for w in "AB":
+            _build_convnet(st, f"vae_encoder_block_{w}.", veb_convs(latent_dim), dtype, False)
+        for w in "AB":
+            _build_convnet(st, f"vae_decoder_block_{w}.", vdb_convs(latent_dim), dtype, False)
+        _build_convnet(st, "decoder_A.", DECODER_CONVS, dtype)
+        _build_convnet(st, "decoder_B.", DECODER_CONVS, dtype)
+        for k in ([f"encoder.{n}" for n, *_ in ENCODER_CONVS] +
+                  [f"vae_encoder_block_{w}.{n}" for w in "AB" for n, *_ in veb_convs(latent_dim)] +
+                  [f"vae_decoder_block_{w}.{n}" for w in "AB" for n, *_ in vdb_convs(latent_dim)] +
+                  [f"decoder_{w}.{n}" for w in "AB" for n, *_ in DECODER_CONVS]):
+            _kaiming(st, k)
     elif arch == "cyclevaegan":                 # Networks.py:1874-1883
         _build_vae(st, "F.", latent_dim, dtype)
         _build_vae(st, "G.", latent_dim, dtype)
@@ -228,19 +253,77 @@ def param_keys(state, prefixes):
 
 
 # --------------------------------------------------------------------------- #
+# bf16 emulation: where the sm_100a tensor-core path rounds
+# --------------------------------------------------------------------------- #
+# In bf16 mode the kernels (vae-cyclegan-implementation_b200/csrc) keep fp32 master weights, fp32
+# accumulators, fp32 InstanceNorm statistics, fp32 losses and fp32 Adam, and round to bfloat16 exactly here:
+#   (r1) a network's NCHW fp32 input when it is packed to NHWC (pack_nchw);
+#   (r2) each filter when it is packed for the GEMM (wpack_multi): forward value only, the weight gradient
+#        accumulates and stays fp32;
+#   (r3) each conv output after bias and the fused pre-norm activation, when the epilogue stores it -- except the
+#        final image layer and the mu / second logvar conv, which are stored in fp32;
+#   (r4) each conv INPUT after normalisation / activation / residual, when the transform pass stores it (xform_fwd);
+#        z = mu + eps * std likewise;
+#   and the gradients stored at the same places: dY of every conv (r3, also of the fp32-stored outputs), the
+#   padded-input gradient dXp written by the data-gradient GEMM (after the pad, r5), the gathered gradient g between
+#   the activation derivative and the InstanceNorm backward (r6), and the packed gradient of every network output.
+# `emulate_bf16()` switches the blocks below to insert those roundings (straight-through: the forward value and /
+# or the passing gradient is rounded to the nearest bfloat16, ties to even, like cvt.rn.bf16.f32).
+_EMU = [False]
+
+
+class emulate_bf16:
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        self.prev, _EMU[0] = _EMU[0], self.on
+
+    def __exit__(self, *exc):
+        _EMU[0] = self.prev
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+class _Round(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, fwd, bwd):
+        ctx.bwd = bwd
+        return _bf(x) if fwd else x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (_bf(g) if ctx.bwd else g), None, None
+
+
+def r_both(x):       # stored activation: value and its gradient are bf16 tensors
+    return _Round.apply(x, True, True) if _EMU[0] else x
+
+
+def r_fwd(x):        # packed filter
+    return _Round.apply(x, True, False) if _EMU[0] else x
+
+
+def r_bwd(x):        # fp32-stored value whose gradient is a bf16 tensor
+    return _Round.apply(x, False, True) if _EMU[0] else x
+
+
+# --------------------------------------------------------------------------- #
 # forward blocks
 # --------------------------------------------------------------------------- #
 def conv_reflect(x, w, b, stride=1, pad=1):
     """nn.Conv2d(padding_mode='reflect') = F.conv2d(F.pad(x, reflect), w, b, stride, 0)
     (torch/nn/modules/conv.py:534-550)."""
     if pad:
-        x = F.pad(x, (pad, pad, pad, pad), mode="reflect")
-    return F.conv2d(x, w, b, stride)
+        x = r_bwd(F.pad(x, (pad, pad, pad, pad), mode="reflect"))                  # (r5)
+    return F.conv2d(x, r_fwd(w), b, stride)                                         # (r2)
 
 
 def inorm(x):
     """nn.InstanceNorm2d defaults: affine=False, no running stats, eps=1e-5, biased var."""
-    return F.instance_norm(x, eps=1e-5)
+    return r_bwd(F.instance_norm(x, eps=1e-5))                                      # (r6)
 
 
 def _cw(P, key):
@@ -249,51 +332,56 @@ def _cw(P, key):
 
 def encoder(P, pre, x):
     """Networks.py:154-181 with blocks 57-116."""
-    h = F.relu(inorm(conv_reflect(x, *_cw(P, pre + "model.0.conv"), 1, 3)))       # CaSb: conv, IN, ReLU
+    x = r_both(x)                                                                   # (r1)
+    h = r_both(conv_reflect(x, *_cw(P, pre + "model.0.conv"), 1, 3))                # CaSb: conv, IN, ReLU   (r3)
+    h = r_both(F.relu(inorm(h)))                                                    # (r4)
     for i in (1, 2, 3, 4):                                                          # D: unshuffle, conv, ReLU, IN
-        h = inorm(F.relu(conv_reflect(F.pixel_unshuffle(h, 2), *_cw(P, pre + f"model.{i}.conv"))))
+        h = r_both(F.relu(conv_reflect(F.pixel_unshuffle(h, 2), *_cw(P, pre + f"model.{i}.conv"))))
+        h = r_both(inorm(h))
     return res_block(P, pre + "model.5.", h)
 
 
 def res_block(P, pre, x):
     """R (Networks.py:98-116): conv1, ReLU, IN, conv2, IN, + residual."""
-    h = inorm(F.relu(conv_reflect(x, *_cw(P, pre + "conv1"))))
-    h = inorm(conv_reflect(h, *_cw(P, pre + "conv2")))
-    return h + x
+    h = r_both(inorm(r_both(F.relu(conv_reflect(x, *_cw(P, pre + "conv1"))))))
+    h = inorm(r_both(conv_reflect(h, *_cw(P, pre + "conv2"))))
+    return r_both(h + x)
 
 
 def decoder(P, pre, z):
     """Networks.py:183-199."""
     h = res_block(P, pre + "model.0.", z)
     for i in (1, 2, 3, 4):                                                          # U: shuffle, conv, ReLU, IN
-        h = inorm(F.relu(conv_reflect(F.pixel_shuffle(h, 2), *_cw(P, pre + f"model.{i}.conv"))))
-    return conv_reflect(h, *_cw(P, pre + "model.5.conv"), 1, 3)                     # CaSb Identity, no norm
+        h = r_both(F.relu(conv_reflect(F.pixel_shuffle(h, 2), *_cw(P, pre + f"model.{i}.conv"))))
+        h = r_both(inorm(h))
+    return r_bwd(conv_reflect(h, *_cw(P, pre + "model.5.conv"), 1, 3))              # CaSb Identity, no norm; fp32 store
 
 
-def ae_forward(P, pre, x):
-    return decoder(P, pre + "decoder.", encoder(P, pre + "encoder.", x))
+def ae_forward(P, pre, x, dec="decoder."):
+    return decoder(P, pre + dec, encoder(P, pre + "encoder.", x))
 
 
 def veb(P, pre, h, eps=None):
     """VariationalEncoderBlock.forward (Networks.py:219-227)."""
-    mu = conv_reflect(h, *_cw(P, pre + "muConv.conv"))
-    lv = conv_reflect(h, *_cw(P, pre + "logvarConv.0.conv"))
-    lv = conv_reflect(lv, *_cw(P, pre + "logvarConv.1.conv"))
+    mu = r_bwd(conv_reflect(h, *_cw(P, pre + "muConv.conv")))                       # fp32 store
+    lv = r_both(conv_reflect(h, *_cw(P, pre + "logvarConv.0.conv")))
+    lv = r_bwd(conv_reflect(lv, *_cw(P, pre + "logvarConv.1.conv")))                # fp32 store
     lv = torch.clamp(lv, min=-10, max=10)
     std = torch.exp(0.5 * lv)
     if eps is None:
         eps = torch.randn_like(std)
     elif callable(eps):
         eps = eps(std)
-    return mu + eps * std, mu, lv
+    return r_both(mu + eps * std), mu, lv
 
 
-def vae_forward(P, pre, x, eps=None):
+def vae_forward(P, pre, x, eps=None, veb_pre="variational_encoder_block.", vdb_pre="variational_decoder_block.",
+                dec="decoder."):
     """VariationalAutoencoder.forward (Networks.py:885-890) -> (Gx, mu, logvar)."""
     h = encoder(P, pre + "encoder.", x)
-    z, mu, lv = veb(P, pre + "variational_encoder_block.", h, eps)
-    h = conv_reflect(z, *_cw(P, pre + "variational_decoder_block.conv.conv"))
-    return decoder(P, pre + "decoder.", h), mu, lv
+    z, mu, lv = veb(P, pre + veb_pre, h, eps)
+    h = r_both(conv_reflect(z, *_cw(P, pre + vdb_pre + "conv.conv")))
+    return decoder(P, pre + dec, h), mu, lv
 
 
 def spectral_weight(P, pre, training=True):
@@ -313,10 +401,12 @@ def spectral_weight(P, pre, training=True):
 
 def discriminator(P, pre, x, training=True):
     """Networks.py:240-269."""
-    h = F.leaky_relu(conv_reflect(x, *_cw(P, pre + "model.0.conv"), 2, 1), 0.2)
+    x = r_both(x)
+    h = r_both(F.leaky_relu(conv_reflect(x, *_cw(P, pre + "model.0.conv"), 2, 1), 0.2))
     for i in (1, 2, 3):
-        h = F.leaky_relu(inorm(conv_reflect(h, *_cw(P, pre + f"model.{i}.conv"), 2, 1)), 0.2)
-    w = spectral_weight(P, pre + "model.4.", training)
+        h = r_both(conv_reflect(h, *_cw(P, pre + f"model.{i}.conv"), 2, 1))
+        h = r_both(F.leaky_relu(inorm(h), 0.2))
+    w = spectral_weight(P, pre + "model.4.", training)                              # fp32 head: a dot product, not a GEMM
     return F.conv2d(h, w, P[pre + "model.4.bias"]).view(-1, 1).squeeze(1)
 
 
@@ -368,8 +458,11 @@ class RefModel:
     """
 
     def __init__(self, arch, latent_dim=64, paired=False, state=None, dtype=torch.float32,
-                 lr=2e-4, betas=(0.5, 0.999), lambdas=None, eps_source=None):
+                 lr=2e-4, betas=(0.5, 0.999), lambdas=None, eps_source=None, emulate_bf16=False, device=None):
+        """emulate_bf16: round like the sm_100a tensor-core path (see "bf16 emulation" above); device: where the
+        tensors live (the GPU parity tests run this checker on the box's GPU in fp32 at the BASELINE batch sizes)."""
         self.arch = canonical_arch(arch)
+        self.emulate = bool(emulate_bf16)
         self.latent_dim = latent_dim
         self.paired = paired
         self.lam = dict(DEFAULT_LAMBDAS)
@@ -378,13 +471,15 @@ class RefModel:
         self.P = OrderedDict()
         for k, v in st.items():
             t = v.detach().to(dtype).clone()
+            if device is not None:
+                t = t.to(device)
             if not is_buffer(k):
                 t.requires_grad_(True)
             self.P[k] = t
         self.eps_source = eps_source
         self.training = True
         a = self.arch
-        if a in ("autoencoder", "vae", "cycleae", "cyclevae"):
+        if a in ("autoencoder", "vae", "cycleae", "cyclevae", "doubleae", "doublevae"):
             # Adam(self.parameters()) -- Networks.py:312, 894, 1372, 1498
             self.opt_G = torch.optim.Adam([self.P[k] for k in param_keys(self.P, [""])], lr=lr, betas=betas)
             self.opt_D = None
@@ -415,7 +510,19 @@ class RefModel:
 
     # -- forward with the reference's return orders ---------------------------
     def forward(self, x, y=None):
+        with emulate_bf16(self.emulate):
+            return self._forward(x, y)
+
+    def _forward(self, x, y=None):
         a = self.arch
+        if a == "doubleae":                                # Networks.py:447-466
+            return ae_forward(self.P, "", x, "decoder_A."), ae_forward(self.P, "", y, "decoder_B.")
+        if a == "doublevae":                               # Networks.py:661-685 (noise drawn for A, then for B)
+            Gx, mu_x, lv_x = vae_forward(self.P, "", x, self.eps_source, "vae_encoder_block_A.",
+                                         "vae_decoder_block_A.", "decoder_A.")
+            Gy, mu_y, lv_y = vae_forward(self.P, "", y, self.eps_source, "vae_encoder_block_B.",
+                                         "vae_decoder_block_B.", "decoder_B.")
+            return Gx, Gy, mu_x, lv_x, mu_y, lv_y
         if a == "autoencoder":
             return ae_forward(self.P, "", x)
         if a == "vae":
@@ -461,7 +568,37 @@ class RefModel:
 
     # -- training steps -------------------------------------------------------
     def training_step(self, batch):
-        return getattr(self, "_step_" + self.arch)(batch["x"], batch["y"])
+        with emulate_bf16(self.emulate):
+            return getattr(self, "_step_" + self.arch)(batch["x"], batch["y"])
+
+    def translate(self, x, to):
+        """Double models: translate_A_to_B (to='B') / translate_B_to_A (to='A'), Networks.py:468-476, 687-699."""
+        with emulate_bf16(self.emulate):
+            if self.arch == "doubleae":
+                return ae_forward(self.P, "", x, f"decoder_{to}.")
+            return vae_forward(self.P, "", x, self.eps_source, f"vae_encoder_block_{to}.", f"vae_decoder_block_{to}.",
+                               f"decoder_{to}.")[0]
+
+    def _step_doubleae(self, x, y):                        # Networks.py:505-546
+        Gx, Gy = self._forward(x, y)
+        la, lb = l1(Gx, x), l1(Gy, y)
+        total = la + lb
+        self.opt_G.zero_grad()
+        total.backward()
+        self.opt_G.step()
+        return {"G_loss": total.item(), "loss_recon_A": la.item(), "loss_recon_B": lb.item(), "total_loss": total.item()}
+
+    def _step_doublevae(self, x, y):                       # Networks.py:757-799
+        Gx, Gy, mu_x, lv_x, mu_y, lv_y = self._forward(x, y)
+        la, lb = l1(Gx, x), l1(Gy, y)
+        ka, kb = kl_loss(mu_x, lv_x), kl_loss(mu_y, lv_y)
+        lk = ka + kb
+        total = la + lb + self.lam["lambda_kl"] * lk
+        self.opt_G.zero_grad()
+        total.backward()
+        self.opt_G.step()
+        return {"G_loss": total.item(), "loss_recon_A": la.item(), "loss_recon_B": lb.item(), "loss_kl": lk.item(),
+                "loss_kl_A": ka.item(), "loss_kl_B": kb.item(), "total_loss": total.item()}
 
     def _step_autoencoder(self, x, y):                     # Networks.py:334-384
         loss = l1(self.forward(x), y)

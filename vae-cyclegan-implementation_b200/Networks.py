@@ -20,12 +20,14 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import lanes as _lanes
 from . import lib as _L
 from .Losses import (CycleConsistencyLoss, GANLossDiscriminator, GANLossGenerator, IdentityLoss,
                      KLDivergenceLoss, TranslationLoss)
 from .functions import require_cuda, run_plan
 from .optim import FusedAdam
 from .plan import Plan, PlanBuilder, no_wgrad, _STATE
+from . import plan as _plan
 
 _ACTS = {"ReLU": _L.ACT_RELU, "LeakyReLU": _L.ACT_LEAKY, "Identity": _L.ACT_NONE}
 
@@ -71,10 +73,19 @@ class SpectralConvParams(nn.Module):
     def power_iteration(self):
         """One power iteration as every training forward of the reference does
         (torch/nn/utils/spectral_norm.py:92-114).  With a 1 x K matrix it converges in one step:
-        v = +-W/|W|, u = +-1, so sigma = |W| and the kernel's unit-vector form is exact."""
-        wm = self.weight_orig.reshape(self.weight_orig.shape[0], -1)
+        v = +-W/|W|, u = +-1, so sigma = |W| and the kernel's unit-vector form is exact.  u is a normalised
+        1-vector, i.e. exactly +-1, so repeating the iteration on unchanged W, u, v reproduces the same bits:
+        the reference's further iterations within one step (one per discriminator call, Networks.py:1916-1919,
+        2032-2035) are skipped."""
+        w = self.weight_orig
+        key = (w._version, getattr(w, "_vcg_epoch", 0), w.data_ptr(), self.weight_u._version, self.weight_v._version)
+        if self.__dict__.get("_vcg_pi_key") == key:
+            return
+        wm = w.reshape(w.shape[0], -1)
         self.weight_v.copy_(F.normalize(torch.mv(wm.t(), self.weight_u), dim=0, eps=1e-12))
         self.weight_u.copy_(F.normalize(torch.mv(wm, self.weight_v), dim=0, eps=1e-12))
+        self.__dict__["_vcg_pi_key"] = (w._version, getattr(w, "_vcg_epoch", 0), w.data_ptr(), self.weight_u._version,
+                                        self.weight_v._version)
 
 
 def _kaiming_init(module, nonlinearity="relu", a=0.0):
@@ -308,6 +319,39 @@ class _Composite(_PlanModule):
     def enable_debug_mode(self, enabled=True):
         self.debug_mode = enabled
 
+    def _prepack(self):
+        """Refresh every derived weight copy of the model on the CALLING stream, before the lanes fork (lanes.py):
+        one multi-tensor pack launch for all stale filters, the discriminator heads' (h, w, c) weight vectors and
+        their spectral-norm power iteration.  Returns True when every convolution has been planned before, i.e.
+        when no pass of this step will have to create (and pack) a kernel-layout copy on a lane."""
+        mods = self.__dict__.get("_vcg_param_mods")
+        if mods is None:
+            mods = self.__dict__["_vcg_param_mods"] = [m for m in self.modules() if isinstance(m, (ConvParams, SpectralConvParams))]
+        warm, pcs = True, []
+        for m in mods:
+            if isinstance(m, SpectralConvParams):
+                if m.weight_orig.is_cuda:
+                    _plan.head_weight(m)
+                    if self.training:
+                        m.power_iteration()
+                continue
+            cache = m.__dict__.get("_vcg_packed")
+            if not cache:
+                warm = False
+            else:
+                pcs.extend(cache.values())
+        if pcs and pcs[0].holder.weight.is_cuda:
+            _plan.refresh_many(pcs, _STATE["dtype"])
+        return warm
+
+    def _dual(self, device, fresh=True):
+        """lanes.dual region for this model's passes.  fresh=True (forward): prepack first; lanes are used from the
+        second step on (the first one creates and packs the kernel-layout copies inside the passes).
+        fresh=False (backward of the same step): same setting as the forward."""
+        if fresh:
+            self.__dict__["_vcg_dual"] = self._prepack() and torch.device(device).type == "cuda"
+        return _lanes.dual(device, self.__dict__.get("_vcg_dual", False))
+
     def _finish_steps(self):
         """complete optimiser steps whose gradient exchange was left running (data-parallel overlap, dist.py)"""
         for n in ("optimizer", "optimizer_G", "optimizer_D"):
@@ -477,10 +521,17 @@ class VariationalAutoencoder(_Composite):
             return m
 
 
-def _gen_call(g, x):
-    """(Gx, mu, logvar) for a VAE generator, (Gx,) for an AE generator."""
-    out = g(x)
+def _gen_call(g, x, eps=None):
+    """(Gx, mu, logvar) for a VAE generator, (Gx,) for an AE generator.  `eps`: pre-drawn bottleneck noise."""
+    out = g(x) if eps is None else g(x, eps=eps)
     return out if isinstance(out, tuple) else (out,)
+
+
+def _draw_eps(calls):
+    """Bottleneck noise of several VAE passes, drawn up front IN THE REFERENCE'S ORDER (one torch.randn_like per
+    pass, Networks.py:223-226 as called from :1909-1914), so that the passes themselves can be issued in any order
+    and on any lane.  calls: [(generator, input tensor)]; AE generators draw nothing."""
+    return [_vae_eps(g, x) if hasattr(g, "variational_encoder_block") else None for g, x in calls]
 
 
 # ====================================================================== generator + discriminator
@@ -509,8 +560,14 @@ class AEGAN(_PairedGAN):
         self.lambda_gan = self.lambda_identity = 0
 
     def forward(self, x, y):
-        Gx, Gy = self.G(x), self.G(y)
-        return Gx, Gy, self.D(Gx), self.D(y)
+        with self._dual(x.device) as d:          # lane 0: G(x), D(Gx), D(y); lane 1: G(y)
+            with d.lane(0):
+                Gx = self.G(x)
+            with d.lane(1):
+                Gy = self.G(y)
+            with d.lane(0):
+                DGx, Dy = self.D(Gx), self.D(y)
+        return Gx, Gy, DGx, Dy
 
     def configure_loss(self, **kwargs):
         self.loss_trans_fn = TranslationLoss()
@@ -534,7 +591,7 @@ class AEGAN(_PairedGAN):
         x, y = self._xy(batch)
         self.optimizer_G.zero_grad()
         Gx, DGx, Dy, lt, lg, _, _, lid, G_loss = self._g_losses(x, y)
-        with no_wgrad(self.D):                       # D grads of the G step are discarded by the reference
+        with self._dual(x.device, fresh=False), no_wgrad(self.D):     # D grads of the G step are discarded by the reference
             G_loss.backward(retain_graph=True)
         self.optimizer_G.step()
         # D step: the reference re-runs D(Gx.detach()) and D(y) (Networks.py:1110-1112); D's weights have
@@ -572,9 +629,15 @@ class VAEGAN(_PairedGAN):
         self.optimizer_G = self.optimizer_D = None
 
     def forward(self, x, y):
-        Gx, mu, lv = self.G(x)
-        Gy, mu_y, lv_y = self.G(y)
-        return Gx, mu, lv, Gy, mu_y, lv_y, self.D(Gx), self.D(y)
+        e = _draw_eps([(self.G, x), (self.G, y)])
+        with self._dual(x.device) as d:          # lane 0: G(x), D(Gx), D(y); lane 1: G(y)
+            with d.lane(0):
+                Gx, mu, lv = self.G(x, eps=e[0])
+            with d.lane(1):
+                Gy, mu_y, lv_y = self.G(y, eps=e[1])
+            with d.lane(0):
+                DGx, Dy = self.D(Gx), self.D(y)
+        return Gx, mu, lv, Gy, mu_y, lv_y, DGx, Dy
 
     def configure_loss(self, **kwargs):
         self.translation_loss = TranslationLoss()
@@ -602,7 +665,7 @@ class VAEGAN(_PairedGAN):
         Gx, DGx, Dy, lt, lg_real, lg_fake, lid, lk, G_loss = self._g_losses(x, y)
         D_loss, D_real, D_fake = self.gan_loss_disc(Dy, DGx.detach())     # only D(y) trains D (Networks.py:1280)
         self.optimizer_G.zero_grad()
-        with no_wgrad(self.D):                       # zeroed by optimizer_D.zero_grad() in the reference
+        with self._dual(x.device, fresh=False), no_wgrad(self.D):     # zeroed by optimizer_D.zero_grad() in the reference
             G_loss.backward(retain_graph=True)
         self.optimizer_G.step()
         self.optimizer_D.zero_grad()
@@ -642,8 +705,7 @@ class _stop_at_inputs:
 
 # ====================================================================== cycle models
 class _Cycle(_Composite):
-    def _losses_common(self, x, y, outs):
-        raise NotImplementedError
+    pass
 
 
 class CycleAE(_Cycle):
@@ -665,10 +727,17 @@ class CycleAE(_Cycle):
         self.lambda_cycle = 0
 
     def forward(self, x, y):
-        gx = _gen_call(self.G, x)
-        fgx = _gen_call(self.F, gx[0])
-        fy = _gen_call(self.F, y)
-        gfy = _gen_call(self.G, fy[0])
+        # noise in the reference's order: G(x), F(Gx), F(y), G(Fy) (Networks.py:1489-1494)
+        e = _draw_eps([(self.G, x), (self.F, x), (self.F, y), (self.G, y)])
+        with self._dual(x.device) as d:          # lane 0: x -> G -> F; lane 1: y -> F -> G
+            with d.lane(0):
+                gx = _gen_call(self.G, x, e[0])
+            with d.lane(1):
+                fy = _gen_call(self.F, y, e[2])
+            with d.lane(0):
+                fgx = _gen_call(self.F, gx[0], e[1])
+            with d.lane(1):
+                gfy = _gen_call(self.G, fy[0], e[3])
         if not self._vae:
             return gx[0], fgx[0], fy[0], gfy[0]
         return (gx[0], fgx[0], fy[0], gfy[0], gx[1], gx[2], fgx[1], fgx[2], fy[1], fy[2], gfy[1], gfy[2])
@@ -713,7 +782,8 @@ class CycleAE(_Cycle):
         x, y = self._xy(batch)
         _, _, total, named = self._losses(x, y)
         self.optimizer.zero_grad()
-        total.backward()
+        with self._dual(x.device, fresh=False):
+            total.backward()
         self.optimizer.step()
         return self._items(named)
 
@@ -762,22 +832,32 @@ class CycleAEGAN(_Cycle):
 
     def _forward(self, x, y, skip_dead):
         dead = skip_dead and not self.paired
-        gx = _gen_call(self.G, x)
-        gy = self._dead(self.G, y) if dead else _gen_call(self.G, y)
-        fgx = _gen_call(self.F, gx[0])
-        fy = _gen_call(self.F, y)
-        fx = self._dead(self.F, x) if dead else _gen_call(self.F, x)
-        gfy = _gen_call(self.G, fy[0])
-        DYGx, DXFy, DXx, DYy = self.DY(gx[0]), self.DX(fy[0]), self.DX(x), self.DY(y)
+        # noise in the reference's order: G(x), G(y), F(Gx), F(y), F(x), G(Fy) (Networks.py:1909-1914); the dead
+        # passes' draws are made (and dropped) so that the RNG stream is the reference's
+        e = _draw_eps([(self.G, x), (self.G, y), (self.F, x), (self.F, y), (self.F, x), (self.G, y)])
+        none3 = (None, None, None)
+        with self._dual(x.device) as d:
+            # lane 0: x -> G -> F, F(x), both DY passes; lane 1: y -> F -> G, G(y), both DX passes
+            with d.lane(0):
+                gx = _gen_call(self.G, x, e[0])
+            with d.lane(1):
+                fy = _gen_call(self.F, y, e[3])
+            with d.lane(0):
+                fgx = _gen_call(self.F, gx[0], e[2])
+            with d.lane(1):
+                gfy = _gen_call(self.G, fy[0], e[5])
+            with d.lane(1):
+                gy = none3 if dead else _gen_call(self.G, y, e[1])
+            with d.lane(0):
+                fx = none3 if dead else _gen_call(self.F, x, e[4])
+            with d.lane(0):
+                DYGx, DYy = self.DY(gx[0]), self.DY(y)
+            with d.lane(1):
+                DXFy, DXx = self.DX(fy[0]), self.DX(x)
         if not self._vae:
             return gx[0], fgx[0], fy[0], gfy[0], DYGx, DXFy, DXx, DYy, gy[0], fx[0]
         return (gx[0], fgx[0], fy[0], gfy[0], gx[1], gx[2], fgx[1], fgx[2], fy[1], fy[2], gfy[1], gfy[2],
                 DYGx, DXFy, DXx, DYy, gy[0], fx[0])
-
-    def _dead(self, gen, x):
-        if self._vae:
-            _vae_eps(gen, x)          # consume the RNG exactly like the skipped pass would
-        return (None, None, None)
 
     def configure_optimizers(self, lr=1e-4, betas=(0.5, 0.999)):
         self.optimizer_G = self._adam(list(self.F.parameters()) + list(self.G.parameters()), lr, betas)
@@ -841,14 +921,14 @@ class CycleAEGAN(_Cycle):
         x, y = self._xy(batch)
         self.optimizer_G.zero_grad()
         _, _, d, G_loss, named = self._g_losses(x, y, self.skip_dead_passes)
-        with no_wgrad(self.DX, self.DY):
+        with self._dual(x.device, fresh=False), no_wgrad(self.DX, self.DY):
             G_loss.backward(retain_graph=True)
         self.optimizer_G.step()
         # discriminators: same weights, same inputs => the four D forwards of Networks.py:2032-2035 would
         # reproduce the activations already saved; run only their backward, stopping at the D inputs
         self.optimizer_D.zero_grad()
         D_loss = self._d_losses(d, named)
-        with _stop_at_inputs():
+        with self._dual(x.device, fresh=False), _stop_at_inputs():
             D_loss.backward()
         self.optimizer_D.step()
         DYGx, DXFy, DXx, DYy = d

@@ -19,6 +19,18 @@ extern "C" int vcg_version(void) { return VCG_ABI_VERSION; }
 extern "C" const char* vcg_last_error(void) { return g_err; }
 extern "C" long long vcg_launch_count(void) { return g_vcg_launches.load(); }
 
+static std::atomic<int> g_sm_budget{0};
+extern "C" int vcg_set_sm_budget(int32_t sms) {
+  VCG_REQUIRE(sms >= 0, VCG_E_INVALID, "set_sm_budget: negative budget %d", sms);
+  g_sm_budget.store(sms);
+  return VCG_OK;
+}
+int vcg_gemm_sms() {
+  const int phys = vcg_num_sms(), b = g_sm_budget.load(std::memory_order_relaxed);
+  // pairs of CTAs (cta_group::2 kernels) need an even count
+  return (b > 0 && b < phys) ? (b < 2 ? 2 : b) : phys;
+}
+
 // ---------------------------------------------------------------- cuTensorMapEncodeTiled
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

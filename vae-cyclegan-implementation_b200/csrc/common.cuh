@@ -43,6 +43,10 @@ static inline int vcg_num_sms() {
   return sms;
 }
 
+// SMs a persistent tensor-core kernel may occupy: the physical count, or the budget set through vcg_set_sm_budget()
+// (two independent network passes running on two streams each take half of the machine; abi.cu)
+int vcg_gemm_sms();
+
 // ------------------------------------------------------------------ element traits
 template <typename T> struct Elem;
 template <> struct Elem<float> {

@@ -567,7 +567,7 @@ int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const 
     a.a_tx_bytes = static_cast<uint32_t>(a.tw * a.th) * 128u;
   }
   a.num_m_tiles = d->n * a.tiles_w * a.tiles_h;
-  const int sms = vcg_num_sms();
+  const int sms = vcg_gemm_sms();
   int bn = d->cout_pad < 256 ? d->cout_pad : 256;
   if (bn == 256 && static_cast<long long>(a.num_m_tiles) * (d->cout_pad / 256) < sms) bn = 128;
   if (bn > 64 && (bn % 64) != 0) bn = 64;

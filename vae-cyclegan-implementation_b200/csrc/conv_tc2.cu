@@ -508,7 +508,7 @@ bool vcg_conv2_supported(const vcg_conv_desc* d, int out_f32) {
 int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y, float* stats,
                      cudaStream_t stream) {
   int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
-  const int sms = vcg_num_sms();
+  const int sms = vcg_gemm_sms();
   Conv2Args a{};
   // interior + ring data gradient: flat == 2 promises a zero halo of (kh - 1, kw - 1) around dY; 3 x 3 filters on maps
   // whose interior tiles exactly (16 x 16, 32 x 32, 64 x 64), no statistics

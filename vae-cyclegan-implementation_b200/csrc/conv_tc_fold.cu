@@ -282,7 +282,7 @@ int vcg_conv_fwd_tc_fold(const vcg_conv_desc* d, const void* x, const void* w, c
   FoldGeom g;
   VCG_REQUIRE(fold_geometry(d, &g), VCG_E_UNSUPPORTED, "conv_tc_fold: unsupported geometry");
   const int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
-  const int sms = vcg_num_sms();
+  const int sms = vcg_gemm_sms();
   FoldConvArgs a{};
   a.n_img = d->n; a.ho = ho; a.wo = wo;
   a.tile_w_out = 128 - d->kw + 1;

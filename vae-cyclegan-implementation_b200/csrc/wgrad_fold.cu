@@ -249,7 +249,7 @@ int vcg_conv_wgrad_fold(const vcg_conv_desc* d, const void* x, const void* dy, i
     VCG_REQUIRE(e == cudaSuccess, VCG_E_CUDA, "wgrad_fold: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int sms = vcg_num_sms();
+  const int sms = vcg_gemm_sms();
   int grid = sms;
   if (grid > a.units / 8) grid = a.units / 8 > 0 ? a.units / 8 : 1;     // keep the 3-stage warm-up per run amortised
   wgrad_fold_kernel<<<grid, kThreads, smem, stream>>>(tmT, tmU, a);

@@ -197,7 +197,7 @@ int vcg_conv_wgrad_tc(const vcg_conv_desc* d, const void* x, const void* dy, int
   a.n_tiles_per_row = chunks_per_row / nsub;
   a.m_tiles = (d->cout + 127) / 128;
   a.kb_total = d->n * a.tiles_w * a.tiles_h;
-  const int sms = vcg_num_sms();
+  const int sms = vcg_gemm_sms();
   const int base_items = a.m_tiles * d->kh * a.n_tiles_per_row;
   // K splits: as many as keep the item count at or below a whole number of waves (a single extra item would
   // add a full wave: 297 items on 148 SMs take 3 rounds, 288 take 2)

@@ -226,7 +226,7 @@ int vcg_conv_wgrad_tc2(const vcg_conv_desc* d, const void* x, const void* dy, in
   a.n_tiles_per_row = (d->kwc_pad / 64) / 4;
   a.m_tiles = d->cout / 256;
   a.kb_total = d->n * a.tiles_w * a.tiles_h;
-  const int sms = vcg_num_sms();
+  const int sms = vcg_gemm_sms();
   const int npairs_max = sms / 2;
   const int base_items = a.m_tiles * d->kh * a.n_tiles_per_row;
   // K splits: as many as keep the item count at or below a whole number of rounds of the CTA pairs

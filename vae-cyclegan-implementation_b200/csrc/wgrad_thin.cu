@@ -123,7 +123,7 @@ int vcg_conv_wgrad_thin(const vcg_conv_desc* d, const void* x, const void* dy, i
     VCG_REQUIRE(e == cudaSuccess, VCG_E_CUDA, "wgrad_thin: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  int grid = vcg_num_sms();      // 246 registers x 256 threads: one persistent CTA per SM
+  int grid = vcg_gemm_sms();      // 246 registers x 256 threads: one persistent CTA per SM
   if (grid > a.ntiles) grid = a.ntiles;
   wgrad_thin_mma_kernel<KH, KW, C><<<grid, C / 8 * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(x),
                                                                      static_cast<const __nv_bfloat16*>(dy), dw, a);

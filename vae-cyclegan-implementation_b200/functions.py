@@ -45,6 +45,8 @@ class PlanFunction(torch.autograd.Function):
         if not _STATE.get("input_grads", True):      # discriminator step: stop at the network inputs
             need = tuple(False for _ in need)
         from .plan import queue_flush
+        from . import lanes
+        lanes.note_stream(torch.cuda.current_stream())      # autograd runs this node on its forward's stream (a lane?)
         gin = ctx.plan.run_backward(ctx.run, grads, need, defer_flush=True)
         queue_flush()       # weight / bias gradient accumulators -> .grad once, after the whole backward pass
         return (None, None, None, None, *gin)

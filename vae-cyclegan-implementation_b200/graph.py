@@ -4,7 +4,12 @@ A CycleVAEGAN step is ~1300 kernel launches; at small per-GPU batch (8 GPUs x ba
 launch path, not the GPU, would set the step time.  GraphedStep captures `model.training_step` once for
 fixed batch shapes -- forward, both backward sweeps (autograd runs at capture time only), the NCCL
 gradient all-reduce, both Adam updates (step counters live on the device, csrc/adam.cu) and the metric
-reductions -- and then replays it: one host call per step, one D2H read of the packed metrics."""
+reductions -- and then replays it: one host call per step, one D2H read of the packed metrics.
+
+The warm-up steps that precede the capture (allocator warm-up, descriptor and table caches) are real training steps;
+their effect is undone before the first replay: parameters, buffers (spectral-norm u / v), Adam moments and step
+counters and the CUDA RNG state are snapshotted first and restored in place afterwards, so a graphed run follows the
+same trajectory as the eager one and a checkpoint's `step` equals the number of batches seen."""
 from __future__ import annotations
 
 import torch
@@ -19,6 +24,11 @@ class GraphedStep:
             raise RuntimeError("GraphedStep: CUDA tensors required")
         self.opts = [o for o in (getattr(model, n, None) for n in ("optimizer", "optimizer_G", "optimizer_D")) if o is not None]
         batch = {"x": self.x, "y": self.y}
+        # two warm-up steps at least: the first one plans and packs inside the passes, the second one takes the
+        # steady-state path (all filters packed by one launch before the lanes fork) and builds its device tables --
+        # host-to-device table copies are not legal inside the capture
+        warmup = max(2, warmup)
+        snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -36,9 +46,45 @@ class GraphedStep:
             model._vcg_capture = None
         for o in self.opts:                              # capture recorded the step but did not execute it
             o.capture_rollback()
+        self._restore(snap)
         self.keys, self.vals = sink["keys"], sink["vals"]
         self._stage_x = self._stage_y = self._copy_stream = self._staged_ready = self._stage_free = None
         self._staged_key = None
+
+    # ---- undo the warm-up steps (in place: every pointer baked into the graph stays valid)
+    def _snapshot(self):
+        snap = {"tensors": [(t, t.detach().clone()) for t in list(self.model.parameters()) + list(self.model.buffers())],
+                "rng": torch.cuda.get_rng_state(self.x.device), "opts": []}
+        for o in self.opts:
+            o.finish()
+            st = {}
+            for p in o._params():
+                s = o.state.get(p) or {}
+                st[p] = {k: v.detach().clone() for k, v in s.items()}
+            snap["opts"].append((o, st, None if o._dev_state is None else o._dev_state.clone(), o._dev_step))
+        return snap
+
+    @torch.no_grad()
+    def _restore(self, snap):
+        for t, saved in snap["tensors"]:
+            t.copy_(saved)
+        for o, st, dev_state, dev_step in snap["opts"]:
+            for p in o._params():
+                cur, old = o.state.get(p) or {}, st[p]
+                for k, v in cur.items():
+                    if k in old:
+                        v.copy_(old[k])
+                    else:
+                        v.zero_()                       # moments / step created by the warm-up: back to "never stepped"
+            if o._dev_state is not None:
+                if dev_state is not None:
+                    o._dev_state.copy_(dev_state)
+                    o._dev_step = dev_step
+                else:
+                    o._dev_state.zero_()
+                    o._dev_step = 0
+        torch.cuda.set_rng_state(snap["rng"], self.x.device)
+        torch.cuda.synchronize()
 
     def __call__(self, batch, prefetch=None):
         """Run one step on `batch`.  `prefetch` (optional) is the NEXT step's batch in pinned host memory: its
@@ -70,7 +116,16 @@ class GraphedStep:
             self._staged_key = self._batch_key(prefetch)
         for o in self.opts:
             o.note_replay()
-        return dict(zip(self.keys, self.vals.tolist()))
+        vals = self.vals.tolist()
+        if not all(v == v and abs(v) != float("inf") for v in vals):
+            # the reference's NaN / Inf guard (Networks.py:356-372) is a host read before the update and cannot run
+            # inside a replayed graph: report after the fact
+            import warnings
+            warnings.warn("GraphedStep: non-finite metric after a replayed step (the update was already applied)")
+            out = dict(zip(self.keys, vals))
+            out["nan_detected"] = True
+            return out
+        return dict(zip(self.keys, vals))
 
     @staticmethod
     def _batch_key(batch):

@@ -264,6 +264,8 @@ def queue_flush():
 
     def cb():
         _FLUSH_QUEUED[0] = False
+        from . import lanes
+        lanes.join_dirty()          # backward nodes ran on the lanes of their forward passes (lanes.py)
         flush_grads()
     torch.autograd.Variable._execution_engine.queue_callback(cb)
 
