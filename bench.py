@@ -15,11 +15,15 @@ Prints ONE JSON line (rank 0).  `value` times the step with the batch already re
 `e2e` times the same public API call with the batch in pinned host memory (every step copies its
 100 MB batch host-to-device inside the timed region and reads the metrics back; with CUDA-graph replay the
 copy of step i+1 is issued on a side stream during step i, GraphedStep(..., prefetch=), like a pinned-memory
-data loader would).  `roofline` is for the dominant kernel family (the tcgen05 implicit
-GEMM conv_tc_kernel, forward + data-gradient launches): algorithmic FLOPs (2*M*N*K with the
-reference's logical dims) / CUDA-event duration of those launches inside the timed region, against the
-measured sustained bf16 peak.  `cpu_baseline` is the oracle port of the reference's training_step on
-the host cores (bounded sample)."""
+data loader would).  `roofline` is for the dominant kernel family (the tcgen05 implicit-GEMM convolution
+kernels: forward, data-gradient AND weight-gradient launches, thin 7x7 fold kernels included): algorithmic
+FLOPs (2*M*N*K with the reference's logical dims) / CUDA-event duration of those launches, measured INSIDE the
+graph-replayed timed region (external events captured into the graph, read after the last timed step), against
+the measured sustained bf16 peak; per-family figures are reported next to it.  `cpu_baseline` / `--impl
+reference` time the UNMODIFIED reference's training_step (oracle/ref_loader.py: /root/reference or the archive
+oracle/build_ref.py made; the oracle port only if neither exists) on the host cores (bounded sample).
+`gpu_reference` (informational) times the same unmodified reference modules through stock PyTorch on the same
+B200 (fp32 with TF32 as shipped, and bf16 autocast + channels_last), at the largest batch that fits."""
 import argparse
 import json
 import os
@@ -47,7 +51,14 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=2, help="bounded CPU sample: batch of the reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=1, help="1: independent passes of the step on two streams (vcg_b200.lanes)")
+    ap.add_argument("--lanes", type=int, default=-1,
+                    help="independent passes of the step on two streams (vcg_b200.lanes): 1 on, 0 off, -1 auto "
+                         "(on when the per-GPU batch is small enough for sub-wave layers: <= 16)")
+    ap.add_argument("--gpu-reference", type=int, default=-1,
+                    help="time the unmodified reference through stock PyTorch on this GPU (informational): 1 on, 0 off, "
+                         "-1 auto (on for the single-GPU run)")
+    ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32"], help="gradient all-reduce element type")
+    ap.add_argument("--profile", type=int, default=1, help="1: external CUDA events around every launch inside the captured graph")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (vcg_b200.graph.GraphedStep)")
     return ap.parse_args()
 
@@ -98,13 +109,29 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def reference_model(device="cpu"):
+    """-> (model with training_step, kind, origin).  kind 'reference': the UNMODIFIED reference class
+    (Networks.CycleVAEGAN, Networks.py:1872-2150); 'port': the oracle restatement of it (same ATen ops)."""
+    import torch
+    from oracle import ref_loader
+    from oracle import ref_port as rp
+    net, origin = ref_loader.load()
+    torch.manual_seed(1234)
+    if net is not None:
+        m = net.CycleVAEGAN(paired=False).to(device)
+        m.configure_optimizers(lr=2e-4)
+        m.configure_loss(lambda_kl=1e-5, lambda_gan=1.0, lambda_identity=5.0, lambda_cycle=10.0, lambda_recon=1.0)
+        m.train()
+        return m, "reference", origin
+    return rp.RefModel("cyclevaegan", paired=False, lr=2e-4, device=None if device == "cpu" else device), "port", origin
+
+
 def cpu_step_time(batch, steps, warmup):
-    """The reference's training_step (oracle port, same ATen ops) on the host cores."""
+    """The reference's own training_step on the host cores (all of them)."""
     import torch
     from oracle import ref_port as rp
     torch.set_num_threads(os.cpu_count())
-    torch.manual_seed(1234)
-    model = rp.RefModel("cyclevaegan", paired=False, lr=2e-4)
+    model, kind, origin = reference_model("cpu")
     b = rp.synthetic_batch(batch)
     for _ in range(warmup):
         model.training_step(b)
@@ -113,7 +140,53 @@ def cpu_step_time(batch, steps, warmup):
         t0 = time.perf_counter()
         model.training_step(b)
         ts.append(time.perf_counter() - t0)
-    return ts, torch.get_num_threads()
+    return ts, torch.get_num_threads(), kind, origin
+
+
+def gpu_reference(dev, global_batch):
+    """Stock PyTorch on the same GPU: the unmodified reference modules, .to(cuda), training_step (train.py:385, 91-97).
+    Two modes: as shipped (fp32 tensors, cuDNN TF32 allowed by default) and bf16 autocast + channels_last.
+    Largest batch <= global_batch that fits; informational (the reference publishes no GPU number)."""
+    import torch
+    from oracle import ref_port as rp
+    out = {}
+    for mode in ("fp32_tf32_default", "bf16_autocast_channels_last"):
+        b = global_batch
+        while b >= 1:
+            model = None
+            try:
+                torch.cuda.empty_cache()
+                model, kind, origin = reference_model(dev)
+                if mode.startswith("bf16") and kind == "reference":
+                    model = model.to(memory_format=torch.channels_last)
+                batch = {k: v.to(dev) for k, v in rp.synthetic_batch(b).items()}
+
+                def step():
+                    if mode.startswith("bf16"):
+                        with torch.autocast("cuda", dtype=torch.bfloat16):
+                            return model.training_step(batch)
+                    return model.training_step(batch)
+                step()
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    step()
+                    torch.cuda.synchronize()
+                    ts.append(time.perf_counter() - t0)
+                best = min(ts)
+                out[mode] = {"value": b / best, "unit": UNIT, "batch": b, "ms_per_step": 1e3 * best, "kind": kind,
+                             "origin": origin, "timing": "best of 3 steps after 1 warm-up, host clock around synchronize()"}
+                break
+            except torch.cuda.OutOfMemoryError:
+                b //= 2
+            except Exception as e:          # informational block: never fail the bench
+                out[mode] = {"error": f"{type(e).__name__}: {e}"[:200], "batch": b}
+                break
+            finally:
+                del model
+                torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------ reference arm
@@ -121,12 +194,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ts, threads = cpu_step_time(args.cpu_batch, args.steps, args.warmup)
+    ts, threads, kind, origin = cpu_step_time(args.cpu_batch, args.steps, args.warmup)
     total = sum(ts)
     value = args.cpu_batch * len(ts) / total
     sample = (f"CycleVAEGAN(paired=False) training_step, batch {args.cpu_batch} (bounded sample of the global-batch-"
-              f"{args.global_batch} workload), fp32, {threads} host threads, oracle port of the reference (a Python "
-              "reference cannot travel to the GPU box)")
+              f"{args.global_batch} workload), fp32, {threads} host threads, "
+              + (f"the unmodified reference modules ({origin})" if kind == "reference" else "oracle port of the reference"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "strong",
@@ -135,8 +208,8 @@ def run_reference(args):
                                "256x256 training step, global batch %d, per-GPU batch %d" % (args.global_batch, args.global_batch // max(1, args.gpus)),
                    "global_batch": args.global_batch, "parallelism": f"dp{args.gpus}", "latent_dim": 64,
                    "cpu_sample_batch": args.cpu_batch,
-                   "note": "reference arm: the reference's CPU path (oracle port, same ATen ops) on a bounded batch of the same workload"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                   "note": "reference arm: the reference's own CPU path on a bounded batch of the same workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -158,19 +231,23 @@ def run_ours(args):
     lib.load()
     plan.set_precision(args.precision)
     from vcg_b200 import lanes
-    lanes.set_enabled(bool(args.lanes))
     if args.global_batch % world:
         raise SystemExit("global batch must be divisible by the number of GPUs")
     per = args.global_batch // world
+    # two lanes pay when layers cannot fill the machine (16x16 maps at a small per-GPU batch); at batch >= 32 every
+    # GEMM is several waves long and the serial schedule measured the same (80.24 vs 80.37 ms at batch 64)
+    use_lanes = bool(args.lanes) if args.lanes >= 0 else per <= 16
+    lanes.set_enabled(use_lanes)
 
     torch.manual_seed(1234)
     model = N.CycleVAEGAN(paired=False).to(dev)
     model.configure_optimizers(lr=2e-4)
     model.configure_loss(lambda_kl=1e-5, lambda_gan=1.0, lambda_identity=5.0, lambda_cycle=10.0, lambda_recon=1.0)
     model.train()
+    sync = None
     if world > 1:
         vdist.broadcast_state(model)
-        vdist.attach(model)
+        sync = vdist.attach(model, vdist.GradSync(wire=args.wire))
     g = torch.Generator().manual_seed(7)
     x_all = torch.rand(args.global_batch, 3, 256, 256, generator=g)
     y_all = torch.rand(args.global_batch, 3, 256, 256, generator=g)
@@ -216,7 +293,7 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         last = step_resident()
-    # ---- timed region (device-resident inputs), conv GEMM launches instrumented with CUDA events
+    # ---- timed region (device-resident inputs); kernel launches bracketed by CUDA events
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -224,68 +301,80 @@ def run_ours(args):
     if not args.graph:
         ops.prof_begin()
     ms = timed(step_resident, args.steps)
-    records = ops.prof_end() if not args.graph else []
-    launches = lib.launch_count() - n0
-    # ---- end-to-end through the public API with host buffers (right after the resident measurement, same clocks)
+    records, rec_steps = [], 1
     if args.graph:
-        for _ in range(2):
-            step_e2e()
-        ms_e2e = timed(step_e2e, args.steps)
-    if args.graph:
-        # kernels inside a replayed graph are not re-issued by the library, so they are neither counted nor
-        # event-timed there: run the same steps once more eagerly (after the timed region) to count the
-        # launches one step consists of and to time the conv GEMM launches with CUDA events
-        n0 = lib.launch_count()
-        ops.prof_begin()
-        ms_eager = timed(lambda: model.training_step({"x": x_dev, "y": y_dev}), args.steps)
-        records = ops.prof_end()
+        launches = runner.launches_per_step * args.steps
+    else:
+        records = [(k, w, t, s.elapsed_time(e)) for k, w, t, s, e in ops.prof_end()]
         launches = lib.launch_count() - n0
-    if not args.graph:
-        for _ in range(2):
-            step_e2e()
-        ms_e2e = timed(step_e2e, args.steps)
+        rec_steps = args.steps
+    # ---- end-to-end through the public API with host buffers (right after the resident measurement, same clocks)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    if args.graph and args.profile:
+        # roofline leg: the SAME step captured once more with an external CUDA event pair around every kernel launch
+        # (event-record nodes inside the graph, re-recorded by each replay) and replayed right after the timed region.
+        # The timed graph carries no events: 2600 record nodes cost 3 % of a batch-64 step and 14 % of a batch-8 step.
+        prof_runner = GraphedStep(model, {"x": x_dev, "y": y_dev}, warmup=2, profile=True)
+        for _ in range(3):
+            prof_runner({"x": x_dev, "y": y_dev})
+        records = prof_runner.kernel_times()
+        del prof_runner
     clocks = sampler.stop() if rank == 0 else None
     value = args.global_batch * args.steps / (ms / 1e3)
     e2e_value = args.global_batch * args.steps / (ms_e2e / 1e3)
     h2d = 2 * per * 3 * 256 * 256 * 4
     d2h = 4 * len(last)
 
-    # ---- roofline of the dominant kernel family
+    # ---- roofline of the dominant kernel family (every tensor-core convolution launch: forward, data gradient,
+    #      weight gradient, the 7x7 fold kernels), per family next to it
     fam = {}
     layers = {}
-    for kind, flops, tag, s, e in records:
+    for kind, work, tag, dt in records:
         f = fam.setdefault(kind, [0.0, 0.0, 0])
-        dt = s.elapsed_time(e)
-        f[0] += flops
+        f[0] += work
         f[1] += dt
         f[2] += 1
         l = layers.setdefault((kind, tag), [0.0, 0.0, 0])
-        l[0] += flops
+        l[0] += work
         l[1] += dt
         l[2] += 1
     if rank == 0 and os.environ.get("VCG_BENCH_LAYERS"):
         with open(os.environ["VCG_BENCH_LAYERS"], "w") as fh:
             for (kind, tag), v in sorted(layers.items(), key=lambda kv: -kv[1][1]):
                 # conv families: v[0] = FLOPs -> TFLOP/s; xform families: v[0] = bytes -> TB/s (same arithmetic)
-                fh.write(f"{kind:16s} {tag:34s} launches/step {v[2] / args.steps:5.1f}  ms/step {v[1] / args.steps:8.3f}  "
+                fh.write(f"{kind:16s} {tag:34s} launches/step {v[2] / rec_steps:5.1f}  ms/step {v[1] / rec_steps:8.3f}  "
                          f"T(FLOP|B)/s {v[0] / max(v[1], 1e-9) / 1e9:8.2f}\n")
     pk = peaks()
-    tc_flops = sum(fam.get(k, [0, 0, 0])[0] for k in ("conv_fwd", "conv_dgrad"))
-    tc_ms = sum(fam.get(k, [0, 0, 0])[1] for k in ("conv_fwd", "conv_dgrad"))
-    tc_n = sum(fam.get(k, [0, 0, 0])[2] for k in ("conv_fwd", "conv_dgrad"))
+    tc_kinds = [k for k in fam if k.startswith("conv_")]
+    tc_flops = sum(fam[k][0] for k in tc_kinds)
+    tc_ms = sum(fam[k][1] for k in tc_kinds)
+    tc_n = sum(fam[k][2] for k in tc_kinds)
     achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms else 0.0
     traffic, traffic_of = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):     # ncu --set full capture of one representative launch (committed evidence)
         tj = json.load(open(tpath))
         traffic, traffic_of = tj.get("conv_tc_kernel_dram_bytes_per_launch"), tj.get("launch")
-    roofline = {"kernel": "conv_tc2_kernel / conv_tc_kernel (tcgen05 implicit GEMM, CTA-pair and single-CTA: forward + data-gradient launches)",
+    step_ms = ms / args.steps
+    roofline = {"kernel": "tcgen05 implicit-GEMM convolution kernels (conv_tc2_kernel / conv_tc_kernel / conv_tc_fold_kernel forward + "
+                          "data gradient, wgrad_tc2_kernel / wgrad_tc_kernel / wgrad_fold_kernel weight gradient): every launch of a step",
                 "bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_of": traffic_of, "peak_source": pk["source"],
-                "launches_per_step": tc_n / max(1, args.steps), "share_of_step": tc_ms / ms,
+                "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_of": traffic_of,
+                "traffic_source": "static: ncu --set full capture committed under profiles/ (not measured in this run)",
+                "peak_source": pk["source"],
+                "timing": ("external CUDA events around every launch inside a second, instrumented capture of the same step, "
+                           "replayed right after the timed region (the timed graph itself carries no events)"
+                           if args.graph else "CUDA events around every launch of the timed steps") +
+                          ("; the two lanes run concurrently on half of the SMs each, so a launch's duration is its time on "
+                           "its half of the machine and the family times add up to more than the step" if use_lanes else ""),
+                "launches_per_step": tc_n / max(1, rec_steps), "share_of_step": tc_ms / max(1, rec_steps) / step_ms,
                 "flops_per_launch": tc_flops / max(1, tc_n), "ms_per_launch": tc_ms / max(1, tc_n),
-                "families": {k: {"tflops": v[0] / (v[1] / 1e3) / 1e12 if v[1] else 0.0, "ms_per_step": v[1] / args.steps,
-                                 "launches_per_step": v[2] / args.steps} for k, v in fam.items()}}
+                "whole_step_tflops": 57.8e12 * (args.global_batch / 64.0) / world / (step_ms / 1e3) / 1e12,
+                "families": {k: {"tflops" if k.startswith("conv_") else "tbytes_per_s":
+                                 v[0] / (v[1] / 1e3) / 1e12 if v[1] else 0.0, "ms_per_step": v[1] / rec_steps,
+                                 "launches_per_step": v[2] / rec_steps} for k, v in fam.items()}}
     if rank != 0:
         return
     line = {
@@ -296,9 +385,10 @@ def run_ours(args):
                                "256x256 training step, global batch %d, per-GPU batch %d" % (args.global_batch, per),
                    "global_batch": args.global_batch, "parallelism": f"dp{world}", "latent_dim": 64,
                    "l2": "working set (weights 276 MB bf16 + >10 GB activations per step) exceeds the 126 MB L2; no flush needed",
-                   "dead_passes_skipped": True, "cuda_graph": bool(args.graph), "lanes": bool(args.lanes),
-                   "roofline_timing": ("conv GEMM launches event-timed in an eager re-run of the same steps right after the "
-                                       "graph-replayed timed region" if args.graph else "event-timed inside the timed region")},
+                   "dead_passes_skipped": True, "cuda_graph": bool(args.graph), "lanes": use_lanes,
+                   "gradient_wire": (args.wire if world > 1 else None),
+                   "wire_bytes_per_step_per_rank": (sum(o.flat_grad().numel() for o in (model.optimizer_G, model.optimizer_D)) *
+                                                    (2 if args.wire == "bf16" else 4) if world > 1 else 0)},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "h2d_overlapped_with_previous_step": bool(args.graph)},
@@ -306,12 +396,26 @@ def run_ours(args):
         "clocks": clocks,
         "final_metrics": {k: last[k] for k in ("G_loss", "D_loss", "loss_cycle", "loss_kl")},
     }
+    want_gpu_ref = args.gpu_reference == 1 or (args.gpu_reference < 0 and world == 1)
+    if want_gpu_ref:
+        # free this arm's graph pool and activations first: the reference keeps ~1.6 GB of fp32 activations per pair
+        del runner
+        model = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        line["gpu_reference"] = gpu_reference(dev, args.global_batch)
+        best = max((v.get("value", 0.0) for v in line["gpu_reference"].values()), default=0.0)
+        if best:
+            line["gpu_reference"]["ours_over_best_stock_pytorch"] = value / best
     if world == 1 and not args.no_cpu_baseline:
-        ts, threads = cpu_step_time(args.cpu_batch, 6, 1)      # ~11 s of CPU work on the box's 16 host threads
+        ts, threads, kind, origin = cpu_step_time(args.cpu_batch, 6, 1)      # ~11 s of CPU work on the box's host threads
         v = args.cpu_batch * len(ts) / sum(ts)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
                                 "sample": f"CycleVAEGAN(paired=False) training_step, batch {args.cpu_batch}, fp32, 1 warm-up + "
-                                          f"{len(ts)} timed steps ({sum(ts):.1f} s) of the oracle port on the host cores"}
+                                          f"{len(ts)} timed steps ({sum(ts):.1f} s) of " +
+                                          (f"the unmodified reference modules ({origin})" if kind == "reference"
+                                           else "the oracle port") + " on the host cores"}
     print(json.dumps(line), flush=True)
 
 

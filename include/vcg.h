@@ -37,7 +37,8 @@ extern "C" {
 
 enum { VCG_OK = 0, VCG_E_INVALID = -1, VCG_E_UNSUPPORTED = -2, VCG_E_CUDA = -3, VCG_E_DRIVER = -4 };
 enum { VCG_F32 = 0, VCG_BF16 = 1 };
-enum { VCG_ACT_NONE = 0, VCG_ACT_RELU = 1, VCG_ACT_LEAKY = 2 };          /* LeakyReLU slope 0.2 */
+enum { VCG_ACT_NONE = 0, VCG_ACT_RELU = 1, VCG_ACT_LEAKY = 2,           /* LeakyReLU slope 0.2 */
+       VCG_ACT_TANH = 3, VCG_ACT_SIGMOID = 4 };                          /* CaSb's other choices, Networks.py:63-71 */
 /* vcg_xform_* addressing modes (destination domain of the forward transform) */
 enum { VCG_MODE_PLAIN = 0,      /* dst[h,w,c]            = src[h,w,c]                              */
        VCG_MODE_SHUFFLE = 1,    /* dst[2h+i,2w+j,c]      = src[h,w,c*4+i*2+j]   (nn.PixelShuffle)   */

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(vcg):
     assert declared <= exported, declared - exported
     assert set(lib.EXPORTS) == declared, set(lib.EXPORTS) ^ declared
     l = lib.load()
-    assert l.vcg_version() == 1
+    assert l.vcg_version() == 2
     assert l.vcg_launch_count() == 0
     assert isinstance(l.vcg_last_error(), bytes)
 

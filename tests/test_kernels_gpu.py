@@ -55,6 +55,8 @@ XF_CASES = [  # (mode, pad, c, h, w, norm, act, res)
     (0, 3, 64, 64, 48, True, 0, False), (2, 1, 64, 64, 64, True, 0, False), (1, 1, 128, 24, 40, True, 0, True),
     (3, 1, 64, 32, 64, False, 2, False), (0, 1, 512, 16, 16, True, 0, True), (2, 1, 24, 16, 16, True, 0, False),
     (0, 2, 8, 6, 5, False, 0, False),
+    # CaSb's Tanh / Sigmoid after the norm (generic gather kernel: derivative from the recomputed pre-activation)
+    (0, 1, 64, 16, 16, True, 3, False), (0, 3, 16, 32, 32, True, 4, False),
 ]
 
 

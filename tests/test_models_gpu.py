@@ -43,7 +43,8 @@ def build_pair(N, rp, arch, cls, seed=1234, **kw):
 
 
 CLS = {"autoencoder": "Autoencoder", "vae": "VariationalAutoencoder", "aegan": "AEGAN", "vaegan": "VAEGAN",
-       "cycleae": "CycleAE", "cyclevae": "CycleVAE", "cycleaegan": "CycleAEGAN", "cyclevaegan": "CycleVAEGAN"}
+       "cycleae": "CycleAE", "cyclevae": "CycleVAE", "cycleaegan": "CycleAEGAN", "cyclevaegan": "CycleVAEGAN",
+       "doubleae": "DoubleAutoencoder", "doublevae": "DoubleVariationalAutoencoder"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -190,7 +191,7 @@ def allowed(prec, step, key, v64, ref_fp32_dev, ref_bf16_rel_dev):
 
 
 GOLD_CASES = ["autoencoder", "vae", "aegan", "vaegan", "cycleae", "cycleae_paired", "cyclevae", "cyclevae_paired",
-              "cycleaegan", "cycleaegan_paired", "cyclevaegan", "cyclevaegan_paired"]
+              "cycleaegan", "cycleaegan_paired", "cyclevaegan", "cyclevaegan_paired", "doubleae", "doublevae"]
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -388,3 +389,140 @@ def test_double_models_train_and_convert(env, name):
     cyc = m.create_cycle_ae() if name == "DoubleAutoencoder" else m.create_cycle_vae()
     assert torch.equal(cyc.G.encoder.state_dict()["model.0.conv.weight"], m.encoder.state_dict()["model.0.conv.weight"])
     assert torch.equal(cyc.F.decoder.state_dict()["model.5.conv.weight"], m.decoder_A.state_dict()["model.5.conv.weight"])
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("arch", ["cyclevaegan", "vaegan", "cyclevae"])
+def test_lanes_and_bucket_overlap_match_the_serial_step(env, arch):
+    """The concurrent schedule (two lanes, gradient buckets applied on the optimiser's side stream while the backward
+    pass still runs; lanes.py, optim.FusedAdam.track) must compute what the serial schedule computes: three steps in
+    fp32 mode with identical noise, metrics to 1e-4 and weights to a fraction of one Adam step."""
+    N, plan, rp = env
+    from vcg_b200 import lanes
+    plan.set_precision("fp32")
+    N.set_eps_source(cpu_eps_source)
+    batch = {k: v.cuda() for k, v in rp.synthetic_batch(1).items()}
+
+    def run(concurrent):
+        prev = lanes.set_enabled(concurrent)
+        try:
+            torch.manual_seed(1234)
+            kw = {"paired": False} if arch.startswith("cycle") else {}
+            m = getattr(N, CLS[arch])(**kw).cuda()
+            m.configure_optimizers(lr=2e-4)
+            for o in (getattr(m, n, None) for n in ("optimizer", "optimizer_G", "optimizer_D")):
+                if o is not None:
+                    o.overlap = concurrent
+            m.configure_loss(**rp.DEFAULT_LAMBDAS)
+            m.train()
+            out = []
+            for s in range(3):
+                torch.manual_seed(100 + s)
+                out.append(m.training_step(batch))
+            return out, {k: v.detach().clone() for k, v in m.state_dict().items()}
+        finally:
+            lanes.set_enabled(prev)
+
+    ms, ws = run(False)
+    mc, wc = run(True)
+    for a, b in zip(ms, mc):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(a[k])), (arch, k, a[k], b[k])
+    torch.manual_seed(1234)
+    w0 = getattr(N, CLS[arch])(**({"paired": False} if arch.startswith("cycle") else {})).state_dict()
+    for k in ws:
+        if ws[k].dim() < 2:
+            continue
+        moved = rel_l2(ws[k].cpu(), w0[k])
+        assert moved > 0, k
+        assert rel_l2(wc[k], ws[k]) < 0.1 * moved + 1e-7, (arch, k, rel_l2(wc[k], ws[k]), moved)
+    N.set_eps_source(None)
+    plan.set_precision("bf16")
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("act", ["Tanh", "Sigmoid"])
+@pytest.mark.parametrize("norm", [True, False], ids=["norm", "nonorm"])
+def test_casb_tanh_sigmoid(env, prec, act, norm):
+    """CaSb's Tanh / Sigmoid choices (reference Networks.py:63-71; no shipped network uses them): conv -> [IN] -> act,
+    forward and all three gradients against torch in fp64.  With InstanceNorm the activation runs in the transform
+    pass (derivative from the recomputed pre-activation); without, in the conv epilogue (derivative from the output)."""
+    import torch.nn.functional as F
+    N, plan, rp = env
+    plan.set_precision(prec)
+    dt = torch.float32 if prec == "fp32" else torch.bfloat16
+    torch.manual_seed(3)
+    m = N.CaSb(16, 32, 3, stride=1, padding=1, activation=act, use_norm=norm).cuda()
+    with torch.no_grad():
+        m.conv.weight.copy_(m.conv.weight.to(dt).float())
+        m.conv.bias.uniform_(-0.5, 0.5)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 16, 32, 32, generator=g).to(dt).float()
+    G = torch.randn(2, 32, 32, 32, generator=g).to(dt).float()
+    xd = x.double().requires_grad_(True)
+    wd = m.conv.weight.detach().cpu().double().requires_grad_(True)
+    bd = m.conv.bias.detach().cpu().double().requires_grad_(True)
+    r = F.conv2d(F.pad(xd, (1,) * 4, mode="reflect"), wd, bd)
+    if norm:
+        r = F.instance_norm(r, eps=1e-5)
+    r = torch.tanh(r) if act == "Tanh" else torch.sigmoid(r)
+    (r * G.double()).sum().backward()
+    xc = x.cuda().requires_grad_(True)
+    out = m(xc)
+    (out * G.cuda()).sum().backward()
+    tol = 2e-5 if prec == "fp32" else 2e-2
+    assert rel_l2(out.detach().cpu(), r.detach()) < (1e-5 if prec == "fp32" else 6e-3)
+    assert rel_l2(xc.grad.cpu(), xd.grad) < tol
+    assert rel_l2(m.conv.weight.grad.cpu(), wd.grad) < tol
+    if not norm:
+        assert rel_l2(m.conv.bias.grad.cpu(), bd.grad) < tol
+    plan.set_precision("bf16")
+
+
+# ------------------------------------------------------------------------------------------------
+def test_train_epoch_keeps_the_reference_random_stream(env):
+    """SURVEY 8(f1).  The reference's epoch loop runs a display forward in train() mode after EVERY batch
+    (train.py:112-117: more bottleneck noise, another power iteration).  train_epoch() computes only the last one but
+    must leave the random stream, the weights and the returned display output exactly where the per-batch variant does."""
+    N, plan, rp = env
+    import argparse
+    from vcg_b200 import train as T
+    plan.set_precision("fp32")
+    g = torch.Generator().manual_seed(3)
+    batches = [{"x": torch.rand(1, 3, 256, 256, generator=g), "y": torch.rand(1, 3, 256, 256, generator=g)} for _ in range(3)]
+
+    def fresh():
+        torch.manual_seed(21)
+        m = N.VAEGAN().cuda()
+        m.configure_optimizers(lr=2e-4)
+        m.configure_loss(**rp.DEFAULT_LAMBDAS)
+        return m
+
+    # (A) the reference's loop, literally: step, then a full forward, every batch
+    a = fresh().train()
+    torch.manual_seed(50)
+    sums = {}
+    for b in batches:
+        bc = {k: v.cuda() for k, v in b.items()}
+        m = a.training_step(bc)
+        for k, v in m.items():
+            sums[k] = sums.get(k, 0.0) + v
+        with torch.no_grad():
+            out_a = a(bc["x"], bc["y"])[0]
+    rng_a = torch.cuda.get_rng_state()
+    # (B) train_epoch
+    b_model = fresh()
+    torch.manual_seed(50)
+    loss, comps, out_b, lx, ly = T.train_epoch(b_model, batches, torch.device("cuda"), argparse.Namespace(cuda_graph=False))
+    rng_b = torch.cuda.get_rng_state()
+    assert torch.equal(rng_a, rng_b), "train_epoch consumed a different amount of CUDA randomness than the reference's loop"
+    assert set(comps) == set(sums) and abs(loss - sums["G_loss"] / 3) <= 2e-3 * abs(loss)
+    for k in ("loss_trans", "loss_kl", "loss_identity"):
+        assert abs(comps[k] - sums[k] / 3) <= 2e-3 * abs(comps[k]) + 1e-6, (k, comps[k], sums[k] / 3)
+    assert out_b.shape == (1, 3, 256, 256) and torch.equal(lx.cpu(), batches[-1]["x"])
+    assert rel_l2(out_b, out_a) < 2e-2          # same noise, weights equal up to the atomics' order after 3 Adam steps
+    # validate(): eval mode, the reference's 6-tuple
+    vloss, vcomps, gx, fy, vx, vy = T.validate(b_model, batches[:2], torch.device("cuda"))
+    assert not b_model.training and gx.shape == (1, 3, 256, 256) and fy is None and "G_loss" in vcomps and vloss == vloss
+    plan.set_precision("bf16")

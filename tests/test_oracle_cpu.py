@@ -17,7 +17,7 @@ def gold(tag):
 
 
 def test_golden_files_cover_every_architecture():
-    for arch in rp.ARCHS:
+    for arch in rp.ARCHS + rp.DOUBLE_ARCHS:
         g = gold(arch)
         assert g["arch"] == arch and len(g["steps"]) == 2 and "G_loss" in g["steps"][0]
     for arch in ("cycleae", "cyclevae", "cycleaegan", "cyclevaegan"):
@@ -50,6 +50,36 @@ def test_oracle_reproduces_reference_training_metrics():
         assert set(got) == set(ref)
         for k in ref:
             assert got[k] == pytest.approx(ref[k], rel=2e-6), (k, got[k], ref[k])
+
+
+def test_oracle_reproduces_reference_training_metrics_gan_and_double():
+    """the same re-check for a two-optimiser GAN model (AEGAN: generator + discriminator steps, spectral-norm head) and
+    for a shared-encoder pretraining model (DoubleAutoencoder): first step bit-for-bit up to thread-count reordering"""
+    for tag in ("aegan", "doubleae"):
+        g = gold(tag)
+        torch.manual_seed(g["model_seed"])
+        m = rp.RefModel(tag, lr=g["lr"], lambdas=g["lambdas"])
+        batch = rp.synthetic_batch(g["batch"], seed=g["data_seed"])
+        torch.manual_seed(g["eps_seeds"][0])
+        got = m.training_step(batch)
+        assert set(got) == set(g["steps"][0])
+        for k, ref in g["steps"][0].items():
+            assert got[k] == pytest.approx(ref, rel=5e-6, abs=1e-7), (tag, k, got[k], ref)
+
+
+def test_bf16_emulation_is_off_by_default_and_rounds_where_stated():
+    """emulate_bf16: identity when off (the goldens above would catch a leak); when on, stored activations are bf16
+    values, the weight gradient stays fp32 and passing gradients are rounded"""
+    x = torch.randn(1, 3, 32, 32)
+    w = torch.randn(8, 3, 3, 3, requires_grad=True)
+    b = torch.zeros(8)
+    y0 = rp.conv_reflect(x, w, b)
+    with rp.emulate_bf16():
+        y1 = rp.r_both(rp.conv_reflect(rp.r_both(x), w, b))
+        (y1 * torch.randn_like(y1)).sum().backward()
+    assert torch.equal(y1.detach().to(torch.bfloat16).float(), y1.detach()) and not torch.equal(y0, y1.detach())
+    assert not torch.equal(w.grad.to(torch.bfloat16).float(), w.grad)         # fp32 accumulation of the weight gradient
+    assert torch.equal(rp.r_both(x), x) and torch.equal(rp.r_fwd(x), x)       # off again outside the context
 
 
 def test_noise_floor_fixture_is_consistent():

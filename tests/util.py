@@ -61,6 +61,10 @@ def ref_xform(x, mode, pad, norm=False, act=0, residual=None):
         v = F.relu(v)
     elif act == 2:
         v = F.leaky_relu(v, 0.2)
+    elif act == 3:
+        v = torch.tanh(v)
+    elif act == 4:
+        v = torch.sigmoid(v)
     if residual is not None:
         v = v + residual
     if mode == 0:

@@ -44,28 +44,26 @@ def main():
 
     # ---- data parallel
     model = make()
-    sync = vdist.attach(model)
+    vdist.attach(model, vdist.GradSync(wire=os.environ.get("DP_WIRE", "fp32")))
+    model.optimizer_G.keep_grads = True            # read the reduced gradient after the step
     per = gb // world
     rows = slice(rank * per, (rank + 1) * per)
     N.set_eps_source(eps_global(rows))
     state["calls"] = 0
-    # capture the reduced gradient right before the (deferred) update: pre_update_hook joins the all-reduce
-    grabbed = {}
-    orig = model.optimizer_G.pre_update_hook
-
-    def hook(o):
-        orig(o)
-        grabbed["g"] = (o.flat_grad() * o.grad_scale).clone()
-    model.optimizer_G.pre_update_hook = hook
-    m_dp = model.training_step({"x": batch["x"][rows].cuda(), "y": batch["y"][rows].cuda()})
+    steps = int(os.environ.get("DP_STEPS", "1"))
+    for _ in range(steps):
+        m_dp = model.training_step({"x": batch["x"][rows].cuda(), "y": batch["y"][rows].cuda()})
+    g_dp = model.optimizer_G.reduced_grad() * model.optimizer_G.grad_scale
     out = None
     if rank == 0:
         ref = make()
+        ref.optimizer_G.keep_grads = True
         N.set_eps_source(eps_global(slice(0, gb)))
         state["calls"] = 0
-        g1 = {}
-        ref.optimizer_G.pre_step_hook = lambda o: g1.__setitem__("g", o.flat_grad().clone())
-        m_1 = ref.training_step({"x": batch["x"].cuda(), "y": batch["y"].cuda()})
+        for _ in range(steps):
+            m_1 = ref.training_step({"x": batch["x"].cuda(), "y": batch["y"].cuda()})
+        g_1 = ref.optimizer_G.reduced_grad()
+        grabbed, g1 = {"g": g_dp}, {"g": g_1}
         worst = max(abs(m_dp[k] - m_1[k]) / max(abs(m_1[k]), 1e-3) for k in m_1)
         gerr = float((grabbed["g"] - g1["g"]).norm() / g1["g"].norm())
         # weights after the step (generators: deferred Adam; discriminators: immediate)

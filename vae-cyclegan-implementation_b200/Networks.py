@@ -29,7 +29,8 @@ from .optim import FusedAdam
 from .plan import Plan, PlanBuilder, no_wgrad, _STATE
 from . import plan as _plan
 
-_ACTS = {"ReLU": _L.ACT_RELU, "LeakyReLU": _L.ACT_LEAKY, "Identity": _L.ACT_NONE}
+_ACTS = {"ReLU": _L.ACT_RELU, "LeakyReLU": _L.ACT_LEAKY, "Identity": _L.ACT_NONE, "Tanh": _L.ACT_TANH,
+         "Sigmoid": _L.ACT_SIGMOID}
 
 
 # ====================================================================== parameter holders
@@ -37,6 +38,7 @@ class ConvParams(nn.Module):
     """Holds one convolution's master parameters (fp32 OIHW weight + bias) under the names the
     reference's nn.Conv2d uses, initialised with the same RNG consumption (torch/nn/modules/conv.py
     reset_parameters: kaiming_uniform_(a=sqrt(5)) on the weight, then the bias)."""
+    _vcg_holder = True
 
     def __init__(self, in_channels, out_channels, kernel_size):
         super().__init__()
@@ -53,6 +55,7 @@ class ConvParams(nn.Module):
 class SpectralConvParams(nn.Module):
     """spectral_norm(nn.Conv2d(512, 1, 16)) of the reference (Networks.py:248): parameters `bias`,
     `weight_orig`, buffers `weight_u`, `weight_v` in the reference's state_dict order."""
+    _vcg_holder = True
 
     def __init__(self, in_channels, out_channels, kernel_size):
         super().__init__()
@@ -128,9 +131,6 @@ class CaSb(_PlanModule):
         super().__init__()
         if activation not in ("ReLU", "LeakyReLU", "Tanh", "Sigmoid", "Identity"):
             raise NotImplementedError("Activation not implemented")
-        if activation in ("Tanh", "Sigmoid"):
-            raise NotImplementedError(f"{activation}: selectable in the reference but used by none of its networks; "
-                                      "no fused kernel is provided")
         if stride not in (1, 2) or (stride == 2 and kernel_size % 2):
             raise NotImplementedError("CaSb: stride must be 1, or 2 with an even kernel")
         self.conv = ConvParams(in_channels, out_channels, kernel_size)
@@ -294,8 +294,13 @@ class _Composite(_PlanModule):
     """Shared training-loop contract of the reference's composites (Networks.py:9-44)."""
     _two_optimizers = False
 
-    def _adam(self, params, lr, betas):
-        return FusedAdam(list(params), lr=lr, betas=betas)
+    def _adam(self, params, lr, betas, owners=None):
+        """owners: the sub-networks whose backward passes training_step announces to FusedAdam.track() -- their
+        gradient buckets are unpacked / all-reduced / applied while the rest of the step still runs (optim.py)."""
+        opt = FusedAdam(list(params), lr=lr, betas=betas)
+        if owners:
+            opt.set_owners(owners)
+        return opt
 
     def save_optimizer_states(self):
         if self._two_optimizers:
@@ -319,11 +324,21 @@ class _Composite(_PlanModule):
     def enable_debug_mode(self, enabled=True):
         self.debug_mode = enabled
 
+    def _noise_calls(self, x, y=None):
+        """[(generator, input)] of the bottleneck-noise draws one forward() makes, in the reference's order"""
+        return []
+
+    def skip_forward_noise(self, x, y=None):
+        """Consume the random stream exactly like forward(x, y) would, without computing it (train.py's epoch loop
+        skips the reference's per-batch display forward, train.py:112-117, but keeps its RNG consumption)."""
+        _draw_eps(self._noise_calls(x, y))
+
     def _prepack(self):
         """Refresh every derived weight copy of the model on the CALLING stream, before the lanes fork (lanes.py):
         one multi-tensor pack launch for all stale filters, the discriminator heads' (h, w, c) weight vectors and
         their spectral-norm power iteration.  Returns True when every convolution has been planned before, i.e.
         when no pass of this step will have to create (and pack) a kernel-layout copy on a lane."""
+        self._finish_steps()            # the previous step's updates and re-packs ran on the optimisers' side streams
         mods = self.__dict__.get("_vcg_param_mods")
         if mods is None:
             mods = self.__dict__["_vcg_param_mods"] = [m for m in self.modules() if isinstance(m, (ConvParams, SpectralConvParams))]
@@ -414,7 +429,7 @@ class Autoencoder(_Composite):
         return self.decoder.emit(b, self.encoder.emit(b, a))
 
     def configure_optimizers(self, lr=1e-4, betas=(0.5, 0.999), decoder_only=False):
-        self.optimizer = self._adam(self.decoder.parameters() if decoder_only else self.parameters(), lr, betas)
+        self.optimizer = self._adam(self.decoder.parameters() if decoder_only else self.parameters(), lr, betas, [self])
         return self.optimizer
 
     def configure_loss(self, **kwargs):
@@ -435,7 +450,8 @@ class Autoencoder(_Composite):
             nan = float("nan")
             return {"nan_detected": True, "G_loss": nan, "loss_trans": nan, "total_loss": nan}
         self.optimizer.zero_grad()
-        loss.backward()
+        with self.optimizer.track({self: 1}):
+            loss.backward()
         self.optimizer.step()
         return self._items({"G_loss": loss, "loss_trans": loss, "total_loss": loss})
 
@@ -480,8 +496,11 @@ class VariationalAutoencoder(_Composite):
             eps = _vae_eps(self, x)
         return self._run("fwd", [x], build, [eps])
 
+    def _noise_calls(self, x, y=None):
+        return [(self, x)]
+
     def configure_optimizers(self, lr=1e-4, betas=(0.5, 0.999)):
-        self.optimizer = self._adam(self.parameters(), lr, betas)
+        self.optimizer = self._adam(self.parameters(), lr, betas, [self])
         return self.optimizer
 
     def configure_loss(self, **kwargs):
@@ -507,7 +526,8 @@ class VariationalAutoencoder(_Composite):
         x, y = self._xy(batch)
         _, lt, lk, G_loss = self._losses(x, y)
         self.optimizer.zero_grad()
-        G_loss.backward()
+        with self.optimizer.track({self: 1}):
+            G_loss.backward()
         self.optimizer.step()
         return self._items({"G_loss": G_loss, "loss_trans": lt, "loss_kl": lk})
 
@@ -531,7 +551,7 @@ def _draw_eps(calls):
     """Bottleneck noise of several VAE passes, drawn up front IN THE REFERENCE'S ORDER (one torch.randn_like per
     pass, Networks.py:223-226 as called from :1909-1914), so that the passes themselves can be issued in any order
     and on any lane.  calls: [(generator, input tensor)]; AE generators draw nothing."""
-    return [_vae_eps(g, x) if hasattr(g, "variational_encoder_block") else None for g, x in calls]
+    return [_vae_eps(g, x) if getattr(g, "latent_dim", None) else None for g, x in calls]
 
 
 # ====================================================================== generator + discriminator
@@ -539,9 +559,8 @@ class _PairedGAN(_Composite):
     _two_optimizers = True
 
     def configure_optimizers(self, lr=2e-4, betas=(0.5, 0.999)):
-        self.optimizer_G = self._adam(self.G.parameters(), lr, betas)
-        self.optimizer_D = self._adam(self.D.parameters(), lr, betas)
-        self.optimizer_G.overlap = True      # Adam(G) runs beside the discriminator backward (joined in _items)
+        self.optimizer_G = self._adam(self.G.parameters(), lr, betas, [self.G])
+        self.optimizer_D = self._adam(self.D.parameters(), lr, betas, [self.D])
         return self.optimizer_G, self.optimizer_D
 
     def _require(self):
@@ -591,14 +610,15 @@ class AEGAN(_PairedGAN):
         x, y = self._xy(batch)
         self.optimizer_G.zero_grad()
         Gx, DGx, Dy, lt, lg, _, _, lid, G_loss = self._g_losses(x, y)
-        with self._dual(x.device, fresh=False), no_wgrad(self.D):     # D grads of the G step are discarded by the reference
+        # (D grads of the G step are discarded by the reference; G(x) and G(y) both produce G's gradients)
+        with self._dual(x.device, fresh=False), no_wgrad(self.D), self.optimizer_G.track({self.G: 2}):
             G_loss.backward(retain_graph=True)
         self.optimizer_G.step()
         # D step: the reference re-runs D(Gx.detach()) and D(y) (Networks.py:1110-1112); D's weights have
         # not changed, so the activations of the first forward are reused and only D's backward runs again
         self.optimizer_D.zero_grad()
         D_loss, D_real, D_fake = self.loss_gan_disc_fn(Dy, DGx)
-        with _stop_at_inputs():
+        with _stop_at_inputs(), self.optimizer_D.track({self.D: 2}):
             D_loss.backward()
         self.optimizer_D.step()
         return self._items({"G_loss": G_loss, "D_loss": D_loss, "D_loss_real": D_real, "D_loss_fake": D_fake,
@@ -628,8 +648,11 @@ class VAEGAN(_PairedGAN):
         self.debug_info = {}
         self.optimizer_G = self.optimizer_D = None
 
+    def _noise_calls(self, x, y=None):
+        return [(self.G, x), (self.G, y)]
+
     def forward(self, x, y):
-        e = _draw_eps([(self.G, x), (self.G, y)])
+        e = _draw_eps(self._noise_calls(x, y))
         with self._dual(x.device) as d:          # lane 0: G(x), D(Gx), D(y); lane 1: G(y)
             with d.lane(0):
                 Gx, mu, lv = self.G(x, eps=e[0])
@@ -665,11 +688,12 @@ class VAEGAN(_PairedGAN):
         Gx, DGx, Dy, lt, lg_real, lg_fake, lid, lk, G_loss = self._g_losses(x, y)
         D_loss, D_real, D_fake = self.gan_loss_disc(Dy, DGx.detach())     # only D(y) trains D (Networks.py:1280)
         self.optimizer_G.zero_grad()
-        with self._dual(x.device, fresh=False), no_wgrad(self.D):     # zeroed by optimizer_D.zero_grad() in the reference
+        # (D grads of the G step are zeroed by optimizer_D.zero_grad() in the reference)
+        with self._dual(x.device, fresh=False), no_wgrad(self.D), self.optimizer_G.track({self.G: 2}):
             G_loss.backward(retain_graph=True)
         self.optimizer_G.step()
         self.optimizer_D.zero_grad()
-        with _stop_at_inputs():
+        with _stop_at_inputs(), self.optimizer_D.track({self.D: 1}):     # DGx is detached: only D(y) contributes
             D_loss.backward()
         self.optimizer_D.step()
         m = self._items({"G_loss": G_loss, "D_loss": D_loss, "loss_gan_disc_real": D_real, "loss_gan_disc_fake": D_fake,
@@ -726,9 +750,12 @@ class CycleAE(_Cycle):
         self.loss_kl = None
         self.lambda_cycle = 0
 
+    def _noise_calls(self, x, y=None):
+        # the reference's order: G(x), F(Gx), F(y), G(Fy) (Networks.py:1489-1494); Gx has x's shape, Fy has y's
+        return [(self.G, x), (self.F, x), (self.F, y), (self.G, y)]
+
     def forward(self, x, y):
-        # noise in the reference's order: G(x), F(Gx), F(y), G(Fy) (Networks.py:1489-1494)
-        e = _draw_eps([(self.G, x), (self.F, x), (self.F, y), (self.G, y)])
+        e = _draw_eps(self._noise_calls(x, y))
         with self._dual(x.device) as d:          # lane 0: x -> G -> F; lane 1: y -> F -> G
             with d.lane(0):
                 gx = _gen_call(self.G, x, e[0])
@@ -743,7 +770,7 @@ class CycleAE(_Cycle):
         return (gx[0], fgx[0], fy[0], gfy[0], gx[1], gx[2], fgx[1], fgx[2], fy[1], fy[2], gfy[1], gfy[2])
 
     def configure_optimizers(self, lr=1e-4, betas=(0.5, 0.999)):
-        self.optimizer = self._adam(self.parameters(), lr, betas)
+        self.optimizer = self._adam(self.parameters(), lr, betas, [self.F, self.G])
         return self.optimizer
 
     def configure_loss(self, **kwargs):
@@ -782,7 +809,7 @@ class CycleAE(_Cycle):
         x, y = self._xy(batch)
         _, _, total, named = self._losses(x, y)
         self.optimizer.zero_grad()
-        with self._dual(x.device, fresh=False):
+        with self._dual(x.device, fresh=False), self.optimizer.track({self.F: 2, self.G: 2}):
             total.backward()
         self.optimizer.step()
         return self._items(named)
@@ -830,11 +857,14 @@ class CycleAEGAN(_Cycle):
     def forward(self, x, y):
         return self._forward(x, y, skip_dead=False)
 
+    def _noise_calls(self, x, y=None):
+        # the reference's order: G(x), G(y), F(Gx), F(y), F(x), G(Fy) (Networks.py:1909-1914)
+        return [(self.G, x), (self.G, y), (self.F, x), (self.F, y), (self.F, x), (self.G, y)]
+
     def _forward(self, x, y, skip_dead):
         dead = skip_dead and not self.paired
-        # noise in the reference's order: G(x), G(y), F(Gx), F(y), F(x), G(Fy) (Networks.py:1909-1914); the dead
-        # passes' draws are made (and dropped) so that the RNG stream is the reference's
-        e = _draw_eps([(self.G, x), (self.G, y), (self.F, x), (self.F, y), (self.F, x), (self.G, y)])
+        # the dead passes' draws are made (and dropped) so that the RNG stream is the reference's
+        e = _draw_eps(self._noise_calls(x, y))
         none3 = (None, None, None)
         with self._dual(x.device) as d:
             # lane 0: x -> G -> F, F(x), both DY passes; lane 1: y -> F -> G, G(y), both DX passes
@@ -860,9 +890,8 @@ class CycleAEGAN(_Cycle):
                 DYGx, DXFy, DXx, DYy, gy[0], fx[0])
 
     def configure_optimizers(self, lr=1e-4, betas=(0.5, 0.999)):
-        self.optimizer_G = self._adam(list(self.F.parameters()) + list(self.G.parameters()), lr, betas)
-        self.optimizer_D = self._adam(list(self.DX.parameters()) + list(self.DY.parameters()), lr, betas)
-        self.optimizer_G.overlap = True      # Adam(F+G) runs beside the discriminator backward (joined in _items)
+        self.optimizer_G = self._adam(list(self.F.parameters()) + list(self.G.parameters()), lr, betas, [self.F, self.G])
+        self.optimizer_D = self._adam(list(self.DX.parameters()) + list(self.DY.parameters()), lr, betas, [self.DX, self.DY])
         return self.optimizer_G, self.optimizer_D
 
     def configure_loss(self, **kwargs):
@@ -921,14 +950,15 @@ class CycleAEGAN(_Cycle):
         x, y = self._xy(batch)
         self.optimizer_G.zero_grad()
         _, _, d, G_loss, named = self._g_losses(x, y, self.skip_dead_passes)
-        with self._dual(x.device, fresh=False), no_wgrad(self.DX, self.DY):
+        n_gen = 3 if self.paired else 2         # passes per generator that reach the loss (G(y), F(x): identity term only)
+        with self._dual(x.device, fresh=False), no_wgrad(self.DX, self.DY), self.optimizer_G.track({self.F: n_gen, self.G: n_gen}):
             G_loss.backward(retain_graph=True)
         self.optimizer_G.step()
         # discriminators: same weights, same inputs => the four D forwards of Networks.py:2032-2035 would
         # reproduce the activations already saved; run only their backward, stopping at the D inputs
         self.optimizer_D.zero_grad()
         D_loss = self._d_losses(d, named)
-        with self._dual(x.device, fresh=False), _stop_at_inputs():
+        with self._dual(x.device, fresh=False), _stop_at_inputs(), self.optimizer_D.track({self.DX: 2, self.DY: 2}):
             D_loss.backward()
         self.optimizer_D.step()
         DYGx, DXFy, DXx, DYy = d
@@ -1048,6 +1078,9 @@ class DoubleVariationalAutoencoder(_Composite):
             b.output(node, "mu")
             b.output(node, "logvar")
         return self._run(which, [x], build, [_vae_eps(self, x)])
+
+    def _noise_calls(self, x, y=None):
+        return [(self, x), (self, y)]
 
     def forward(self, x, y):
         Gx, mu_x, lv_x = self._pass(x, "A")

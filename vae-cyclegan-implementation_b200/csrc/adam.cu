@@ -55,7 +55,6 @@ adam_multi_kernel(const vcg_adam_chunk* __restrict__ chunks, const float* __rest
       g4 = make_float4(a.x, a.y, b.x, b.y);
     } else {
       g4 = reinterpret_cast<const float4*>(ck.g)[i];
-      if (kZero) reinterpret_cast<float4*>(gz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float4 m = reinterpret_cast<float4*>(ck.m)[i];
     float4 v = reinterpret_cast<float4*>(ck.v)[i];
@@ -71,14 +70,17 @@ adam_multi_kernel(const vcg_adam_chunk* __restrict__ chunks, const float* __rest
     reinterpret_cast<float4*>(ck.p)[i] = p;
     reinterpret_cast<float4*>(ck.m)[i] = m;
     reinterpret_cast<float4*>(ck.v)[i] = v;
+    // (after the arithmetic: a store to the address of a load that is still in flight stalls the thread until the
+    //  load returns -- zeroing right behind the load made this kernel 5x slower)
+    if (!kBf16 && kZero) reinterpret_cast<float4*>(gz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int i = (n4 << 2) + threadIdx.x; i < n; i += 256) {
     const float g = (kBf16 ? __bfloat162float(gb[i]) : ck.g[i]) * grad_scale;
-    if (!kBf16 && kZero) gz[i] = 0.f;
     const float m = lerp_like_torch(ck.m[i], g, w1);
     const float v = ck.v[i] * beta2 + w2 * g * g;
     ck.m[i] = m; ck.v[i] = v;
     ck.p[i] = ck.p[i] - lr_over_bc1 * (m / (sqrtf(v) / bc2_sqrt + eps));
+    if (!kBf16 && kZero) gz[i] = 0.f;
   }
 }
 
@@ -87,13 +89,25 @@ adam_multi_kernel(const vcg_adam_chunk* __restrict__ chunks, const float* __rest
 __global__ void __launch_bounds__(256) cast_bf16_kernel(float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4,
                                                          long long n, int zero_src) {
   const long long stride = static_cast<long long>(gridDim.x) * 256;
-  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += stride) {
-    const float4 v = reinterpret_cast<const float4*>(src)[i];
-    if (zero_src) reinterpret_cast<float4*>(src)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto pack = [](const float4& v) {
     uint2 r;
     *reinterpret_cast<__nv_bfloat162*>(&r.x) = __floats2bfloat162_rn(v.x, v.y);
     *reinterpret_cast<__nv_bfloat162*>(&r.y) = __floats2bfloat162_rn(v.z, v.w);
-    reinterpret_cast<uint2*>(dst)[i] = r;
+    return r;
+  };
+  // two independent 16-byte loads in flight per thread; the zero stores come last (a store to the address of a load
+  // that is still in flight would stall the thread until the load returns)
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += 2 * stride) {
+    const long long j = i + stride;
+    const bool two = j < n4;
+    const float4 a = reinterpret_cast<const float4*>(src)[i];
+    const float4 b = two ? reinterpret_cast<const float4*>(src)[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<uint2*>(dst)[i] = pack(a);
+    if (two) reinterpret_cast<uint2*>(dst)[j] = pack(b);
+    if (zero_src) {
+      reinterpret_cast<float4*>(src)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (two) reinterpret_cast<float4*>(src)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   for (long long i = 4 * n4 + static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += stride) {
     dst[i] = __float2bfloat16_rn(src[i]);

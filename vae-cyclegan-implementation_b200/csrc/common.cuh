@@ -86,13 +86,22 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p,
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == VCG_ACT_RELU) return v > 0.f ? v : 0.f;
   if (act == VCG_ACT_LEAKY) return v > 0.f ? v : 0.2f * v;
+  if (act == VCG_ACT_TANH) return tanhf(v);
+  if (act == VCG_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
   return v;
 }
-// derivative expressed through the activation OUTPUT o (ReLU/LeakyReLU keep the sign)
+// derivative expressed through the activation OUTPUT o (ReLU/LeakyReLU keep the sign; tanh' = 1 - o^2, sigmoid' = o(1-o))
 __device__ __forceinline__ float act_grad(float o, int act) {
   if (act == VCG_ACT_RELU) return o > 0.f ? 1.f : 0.f;
   if (act == VCG_ACT_LEAKY) return o > 0.f ? 1.f : 0.2f;
+  if (act == VCG_ACT_TANH) return 1.f - o * o;
+  if (act == VCG_ACT_SIGMOID) return o * (1.f - o);
   return 1.f;
+}
+// derivative expressed through the activation INPUT z (where the saved tensor is the pre-activation value)
+__device__ __forceinline__ float act_grad_in(float z, int act) {
+  if (act == VCG_ACT_TANH || act == VCG_ACT_SIGMOID) return act_grad(act_apply(z, act), act);
+  return act_grad(z, act);
 }
 // branch-free form for inner loops: slope = act_slope(act) once per kernel, then one compare + select per element
 __device__ __forceinline__ float act_slope(int act) { return act == VCG_ACT_RELU ? 0.f : (act == VCG_ACT_LEAKY ? 0.2f : 1.f); }
@@ -289,6 +298,9 @@ __device__ __forceinline__ void bias_act32(float (&v)[32], const float* __restri
   } else if (act == VCG_ACT_LEAKY) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+  } else if (act == VCG_ACT_TANH || act == VCG_ACT_SIGMOID) {      // CaSb(activation="Tanh"/"Sigmoid"), Networks.py:63-71
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], act);
   }
   if (ncols < 32) {
 #pragma unroll

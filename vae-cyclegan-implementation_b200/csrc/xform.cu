@@ -466,14 +466,14 @@ xform_bwd_generic_kernel(const __grid_constant__ XbArgs p, const T* __restrict__
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float z = (yv[j] - mean[j]) * rstd[j];
-            g[j] *= act_grad(z, p.act);
+            g[j] *= act_grad_in(z, p.act);
             s1[j] += g[j]; s2[j] += g[j] * z;
           }
         } else {
           // no norm: at most one activation (fused in the conv epilogue or applied after): y or act(y) share sign
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            g[j] *= act_grad(yv[j], p.act) * act_grad(yv[j], p.pre_act);
+            g[j] *= act_grad_in(yv[j], p.act) * act_grad(yv[j], p.pre_act);      // y: input of act, output of pre_act
             s1[j] += g[j];
           }
         }
@@ -1085,6 +1085,8 @@ extern "C" int vcg_xform_bwd_gather(const vcg_xbwd_desc* d, const vcg_gsrc* srcs
   const int zc = (d->c / 8 + 31) / 32, hw = d->h * d->w;
   const int cg_total = d->c / 8;
   bool fast = (cg_total & (cg_total - 1)) == 0 && (!d->norm || (reinterpret_cast<uintptr_t>(mean_rstd) & 15) == 0);
+  // the fast kernel knows the piecewise-linear activations only (slope select); tanh / sigmoid take the generic one
+  fast = fast && d->act <= VCG_ACT_LEAKY && d->pre_act <= VCG_ACT_LEAKY;
   for (int k = 0; k < d->nsrc; ++k) fast = fast && (srcs[k].pad == 0 || srcs[k].folded);
   if (fast) {
     XgArgs g{};
@@ -1205,6 +1207,7 @@ extern "C" int vcg_xform_bwd_norm(const vcg_xbwd_desc* d, const void* y, const f
   int rc = fill_xb(d, nullptr, a);
   if (rc) return rc;
   VCG_REQUIRE(d->norm && mean_rstd && gsums, VCG_E_INVALID, "xform_bwd_norm: needs norm statistics");
+  VCG_REQUIRE(d->pre_act <= VCG_ACT_LEAKY, VCG_E_UNSUPPORTED, "xform_bwd_norm: pre-norm activation %d (ReLU / LeakyReLU only)", d->pre_act);
   const int zc = (d->c / 8 + 31) / 32, hw = d->h * d->w;
   const int cg_total = d->c / 8;
   if ((cg_total & (cg_total - 1)) == 0 && (reinterpret_cast<uintptr_t>(mean_rstd) & 15) == 0) {

@@ -16,8 +16,11 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, model, example_batch, warmup=2):
+    def __init__(self, model, example_batch, warmup=2, profile=False):
+        """profile=True: every kernel launch of the captured step is bracketed by external CUDA events (ops.prof_begin)
+        that each replay re-records; kernel_times() reads the last replay's durations (bench.py's roofline)."""
         self.model = model
+        self.records = None
         self.x = example_batch["x"].detach().clone()
         self.y = example_batch["y"].detach().clone()
         if not self.x.is_cuda:
@@ -39,17 +42,31 @@ class GraphedStep:
         sink = {}
         model._vcg_capture = sink
         self.graph = torch.cuda.CUDAGraph()
+        from . import lib, ops
+        if profile:
+            ops.prof_begin(external=True)
+        n0 = lib.launch_count()
         try:
             with torch.cuda.graph(self.graph):
                 model.training_step(batch)
         finally:
             model._vcg_capture = None
+            if profile:
+                self.records = ops.prof_end()
+        self.launches_per_step = lib.launch_count() - n0      # kernels of this library inside one replay
         for o in self.opts:                              # capture recorded the step but did not execute it
             o.capture_rollback()
         self._restore(snap)
         self.keys, self.vals = sink["keys"], sink["vals"]
         self._stage_x = self._stage_y = self._copy_stream = self._staged_ready = self._stage_free = None
         self._staged_key = None
+
+    def kernel_times(self):
+        """[(family, flops or bytes, tag, milliseconds)] of the kernel launches of the LAST replay (profile=True)."""
+        if self.records is None:
+            raise RuntimeError("GraphedStep was built without profile=True")
+        torch.cuda.synchronize()
+        return [(kind, work, tag, s.elapsed_time(e)) for kind, work, tag, s, e in self.records]
 
     # ---- undo the warm-up steps (in place: every pointer baked into the graph stays valid)
     def _snapshot(self):
@@ -83,6 +100,11 @@ class GraphedStep:
                 else:
                     o._dev_state.zero_()
                     o._dev_step = 0
+        # the kernel-layout filter copies still hold the warm-up weights, and the captured step re-packs them only at
+        # its END (behind each bucket's Adam): bring them back to the restored masters before the first replay
+        prepack = getattr(self.model, "_prepack", None)
+        if prepack is not None:
+            prepack()
         torch.cuda.set_rng_state(snap["rng"], self.x.device)
         torch.cuda.synchronize()
 

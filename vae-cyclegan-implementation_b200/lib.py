@@ -11,9 +11,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvcg_b200.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 MODE_PLAIN, MODE_SHUFFLE, MODE_UNSHUFFLE, MODE_PAD_S2D = 0, 1, 2, 3
 WMAP_PLAIN, WMAP_UNSHUFFLE, WMAP_S2D = 0, 1, 2
+ADAM_TICK, ADAM_GRAD_BF16, ADAM_ZERO_GRAD = 1, 2, 4
 
 i32 = C.c_int32
 
@@ -98,7 +99,8 @@ _SIGS = {
     "vcg_dhead_bwd": (C.c_int, [i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "vcg_adam_multi": (C.c_int, [C.c_void_p, i32, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
-                                 C.c_void_p]),
+                                 i32, C.c_void_p]),
+    "vcg_cast_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, i32, C.c_void_p]),
     "vcg_probe_tmap": (C.c_int, [C.c_void_p, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "vcg_zero": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "vcg_zero_halo": (C.c_int, [i32, C.c_void_p, i32, i32, i32, i32, i32, C.c_void_p]),
@@ -119,7 +121,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.vcg_version() != 1:
+        if lib.vcg_version() != 2:
             raise RuntimeError("libvcg_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -17,12 +17,16 @@ def rup(x, m):
 
 
 class _Prof:
-    """Optional CUDA-event instrumentation of the conv GEMM launches (bench.py's roofline leg)."""
+    """Optional CUDA-event instrumentation of the kernel launches (bench.py's roofline leg).  external=True creates
+    the events with cudaEventRecordExternal semantics: recorded while a CUDA graph is being captured they become
+    event-record NODES of the graph, re-recorded by every replay, so the kernels of a replayed step can be timed."""
     records = None
+    external = False
 
 
-def prof_begin():
+def prof_begin(external=False):
     _Prof.records = []
+    _Prof.external = bool(external)
 
 
 def prof_end():
@@ -33,14 +37,14 @@ def prof_end():
 def _rec(kind, flops, tag=""):
     if _Prof.records is None:
         return None
-    s = torch.cuda.Event(enable_timing=True)
+    s = torch.cuda.Event(enable_timing=True, external=_Prof.external)
     s.record()
     return (kind, flops, tag, s)
 
 
 def _rec_end(tok):
     if tok is not None:
-        e = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True, external=_Prof.external)
         e.record()
         _Prof.records.append((*tok, e))
 
@@ -450,10 +454,19 @@ def dhead_bwd(x, w_khwc, wnorm2, gscore, dx, dw, dbias, scratch):
 
 
 @_profiled("adam_multi")
-def adam_multi(chunks_dev, nchunks, state_dev, lr, beta1, beta2, eps, grad_scale=1.0):
-    """state_dev: float32[4] device tensor {step, lr/bc1, sqrt(bc2), -}; the call advances step by one."""
+def adam_multi(chunks_dev, nchunks, state_dev, lr, beta1, beta2, eps, grad_scale=1.0, flags=L.ADAM_TICK):
+    """state_dev: float32[4] device tensor {step, lr/bc1, sqrt(bc2), -}; ADAM_TICK advances step by one."""
     L.check(L.load().vcg_adam_multi(L.ptr(chunks_dev), nchunks, L.ptr(state_dev), lr, beta1, beta2, eps, grad_scale,
-                                    L.stream_ptr()), "vcg_adam_multi")
+                                    flags, L.stream_ptr()), "vcg_adam_multi")
+
+
+@_profiled("cast_bf16")
+def cast_bf16(src, dst, zero_src=False):
+    """dst (bf16) = src (fp32), optionally src = 0: the gradient wire buffer of the data-parallel all-reduce"""
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    assert src.is_contiguous() and dst.is_contiguous()
+    L.check(L.load().vcg_cast_bf16(L.ptr(src), L.ptr(dst), src.numel(), 1 if zero_src else 0, L.stream_ptr()), "vcg_cast_bf16")
+    return dst
 
 
 def probe_tmap(base_tensor, dims, strides_bytes, box):

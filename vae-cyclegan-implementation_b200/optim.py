@@ -1,13 +1,26 @@
 """FusedAdam: torch.optim.Adam's interface (param_groups, state_dict()/load_state_dict() with the
 same keys -- exp_avg, exp_avg_sq, step -- so reference checkpoints interoperate, Networks.py:315-328,
-utils.py:22,47) with the update done by ONE multi-tensor kernel launch (csrc/adam.cu) instead of the
+utils.py:22,47) with the update done by multi-tensor kernel launches (csrc/adam.cu) instead of the
 foreach kernel sequence of torch/optim/adam.py:457-547.
 
-Gradients live in one flat fp32 buffer (``.grad`` tensors are views into it): zero_grad() is a single
-fill, and data-parallel training all-reduces the flat buffer in buckets (dist.py)."""
+Layout.  Gradients live in one flat fp32 buffer (``.grad`` tensors are views into it) and so do the two
+Adam moments.  The parameters are grouped into *buckets*: the convolutions of one generator /
+discriminator (an "owner") in the order in which the backward pass finishes them -- decoder first,
+encoder last -- cut every ~24 M parameters.  A bucket is a contiguous range of the flat buffers.
+
+Overlap (the "bucketed, overlapped with backward" exchange of SURVEY.md 8e).  Inside
+``with optimizer.track({owner: passes})`` the plan's backward reports every weight-gradient GEMM it
+issues; as soon as the last pass that touches a bucket has issued its last contribution, the bucket's
+tail runs on the optimiser's side stream, behind exactly those GEMMs (CUDA events):
+
+    accumulators -> .grad (wunpack_multi)  ->  [fp32 -> bf16 wire cast, NCCL all-reduce]  ->  Adam  ->  filter re-pack
+
+while the main stream / lanes keep running the rest of the backward pass and the discriminator step.
+``step()`` only completes what has not run yet, ``finish()`` joins the side stream.  The Adam kernel
+zeroes the fp32 gradient it consumed, so the next ``zero_grad()`` costs nothing."""
 from __future__ import annotations
 
-import ctypes as C
+import contextlib
 
 import numpy as np
 import torch
@@ -16,161 +29,365 @@ from . import lib as L
 from . import ops
 
 CHUNK = 65536
+BUCKET_PARAMS = 24 << 20
+
+
+class _Bucket:
+    def __init__(self, owner, holders, params):
+        self.owner, self.holders, self.params = owner, holders, params
+        self.lo = self.hi = 0
+        self.tables = {}          # wire mode -> (key, device table, nchunks)
+        self.events = {}          # stream handle -> event behind the last contribution issued on that stream
+        self.fired = False
+        self.remaining = 0
+
+
+class _Tracker:
+    """Counts the weight-gradient contributions of a tracked backward pass (plan.run_backward calls
+    contributed(holder) after it issued the holder's weight-gradient GEMM)."""
+
+    def __init__(self, opt, expect):
+        self.opt = opt
+        self.count = {}
+        self.buckets = []
+        for b in opt._buckets:
+            n = expect.get(b.owner) if b.owner is not None else None
+            if not n or not b.holders:
+                continue
+            b.remaining, b.events, b.fired = len(b.holders), {}, False
+            self.buckets.append(b)
+            for h in b.holders:
+                self.count[id(h)] = [int(n), b]
+
+    def tracks(self, holder):
+        return id(holder) in self.count
+
+    def contributed(self, holder):
+        c = self.count.get(id(holder))
+        if c is None:
+            return
+        b = c[1]
+        if b.fired:
+            raise RuntimeError("FusedAdam.track: a weight gradient arrived after its bucket was handed to the optimiser "
+                               "(more backward passes than announced)")
+        st = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(st)
+        b.events[st.cuda_stream] = ev
+        c[0] -= 1
+        if c[0] == 0:
+            b.remaining -= 1
+            if b.remaining == 0:
+                self.opt._process(b)
+
+    def finish(self):
+        for b in self.buckets:
+            if not b.fired:
+                self.opt._process(b)
 
 
 class FusedAdam(torch.optim.Adam):
-    def state_dict(self):
-        self.finish()
-        return super().state_dict()
-
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, flat_grads=True):
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, foreach=False)
         self._flat_grads = flat_grads
-        self._flat = None
-        self._table = None
-        self._table_key = None
+        self._flat = self._m = self._v = self._wire = None
+        self._offsets = {}
+        self._buckets = None
+        self._owners = None
         self._dev_state = None      # float32[4] on the device: {step, lr/bc1, sqrt(bc2), -}
         self._dev_step = 0
         self._last = None
+        self._ticked = False
+        self._zeroed = False        # the flat gradient buffer is known to hold zeros
+        self.keep_grads = False     # True: .grad survives step() (tests / tools that read gradients after a step)
         self.grad_scale = 1.0       # data-parallel averaging folded into the update (dist.py sets 1/world)
-        self.pre_step_hook = None   # dist.py: starts the all-reduce of the flat gradient buffer (side stream)
-        self.pre_update_hook = None  # dist.py: joins the all-reduce right before the Adam kernel
-        self.defer = False          # dist.py: step() only starts the all-reduce; finish() joins it and updates, so
-                                    # that the exchange overlaps whatever the caller runs in between
-        self._deferred = False
-        self.overlap = False        # single-process two-optimiser models: step() launches the Adam kernel on a side
-                                    # stream so that it overlaps the discriminator backward; finish() joins it
+        self.sync = None            # dist.GradSync when data-parallel
+        self.overlap = True         # run the bucket tails on a side stream (joined by finish())
         self._side = None
-        self._side_pending = False
+        self._side_used = False
 
-    # ---- flat gradient buffer -------------------------------------------------------------
+    # ---- buckets ----------------------------------------------------------------------------
+    def set_owners(self, owners, bucket_params=BUCKET_PARAMS):
+        """owners: the modules (generators / discriminators) whose passes the training step announces to track().
+        Their convolutions are bucketed in backward-completion order (reverse definition order)."""
+        self._owners = list(owners)
+        self._bucket_params = bucket_params
+        self._buckets = None
+        self._flat = None
+
     def _params(self):
         return [p for g in self.param_groups for p in g["params"] if p.requires_grad]
 
+    def _build_buckets(self):
+        mine = {id(p) for p in self._params()}
+        taken = set()
+        buckets = []
+        for owner in self._owners or []:
+            holders = [m for m in owner.modules() if getattr(m, "_vcg_holder", False)]
+            cur_h, cur_p, cur_n = [], [], 0
+            for h in reversed(holders):
+                ps = [p for p in h.parameters(recurse=False) if id(p) in mine and id(p) not in taken]
+                if not ps:
+                    continue
+                n = sum(p.numel() for p in ps)
+                if cur_h and cur_n + n > self._bucket_params:
+                    buckets.append(_Bucket(owner, cur_h, cur_p))
+                    cur_h, cur_p, cur_n = [], [], 0
+                cur_h.append(h)
+                cur_p.extend(ps)
+                cur_n += n
+                taken.update(id(p) for p in ps)
+            if cur_h:
+                buckets.append(_Bucket(owner, cur_h, cur_p))
+        rest = [p for p in self._params() if id(p) not in taken]
+        if rest or not buckets:
+            # parameters outside the announced owners (or no owners at all): one bucket, flushed by plan.flush_grads()
+            buckets.append(_Bucket(None, None, rest))
+        self._buckets = buckets
+
     def flat_grad(self):
-        """Allocate (once) the flat gradient buffer and point every .grad into it."""
+        """Allocate (once) the flat gradient / moment buffers and point every .grad into the gradient buffer."""
         ps = self._params()
         if self._flat is None or self._flat.device != ps[0].device:
-            total = sum((p.numel() + 3) // 4 * 4 for p in ps)     # keep every view 16-byte aligned
-            self._flat = torch.zeros(total, dtype=torch.float32, device=ps[0].device)
+            self._build_buckets()
+            dev = ps[0].device
             off = 0
+            self._offsets = {}
+            for b in self._buckets:
+                b.lo = off
+                for p in b.params:
+                    self._offsets[id(p)] = off
+                    off += (p.numel() + 3) // 4 * 4           # keep every view 16-byte aligned
+                b.hi = off
+                b.tables = {}
+            self._flat = torch.zeros(off, dtype=torch.float32, device=dev)
+            self._m = self._v = self._wire = None
+            self._zeroed = True
             for p in ps:
-                p.grad = self._flat[off:off + p.numel()].view_as(p)
-                off += (p.numel() + 3) // 4 * 4
+                o = self._offsets[id(p)]
+                p.grad = self._flat[o:o + p.numel()].view_as(p)
+                p._vcg_opt = self
         return self._flat
+
+    def wire_buffer(self):
+        """bf16 image of the flat gradient buffer: what travels over NVLink (dist.GradSync)."""
+        if self._wire is None or self._wire.device != self._flat.device:
+            self._wire = torch.zeros(self._flat.numel(), dtype=torch.bfloat16, device=self._flat.device)
+        return self._wire
+
+    def reduced_grad(self):
+        """the gradient the last update consumed (data-parallel: the all-reduced sum), fp32 copy"""
+        src = self._wire if (self.sync is not None and self.sync.world > 1 and self.sync.wire == "bf16") else self._flat
+        return src.float().clone()
+
+    def mark_dirty(self):
+        self._zeroed = False
 
     def zero_grad(self, set_to_none=True):
         self.finish()
-        if not self._flat_grads or not self._params() or not self._params()[0].is_cuda:
+        ps = self._params()
+        if not self._flat_grads or not ps or not ps[0].is_cuda:
             return super().zero_grad(set_to_none)
         flat = self.flat_grad()
-        ops.zero_(flat)
-        off = 0
-        for p in self._params():       # re-attach views dropped by an external zero_grad(set_to_none=True)
-            if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + 4 * off:
-                p.grad = flat[off:off + p.numel()].view_as(p)
-            off += (p.numel() + 3) // 4 * 4
+        if not self._zeroed:
+            ops.zero_(flat)
+            self._zeroed = True
+        for p in ps:       # re-attach views dropped by an external zero_grad(set_to_none=True)
+            o = self._offsets[id(p)]
+            if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + 4 * o:
+                p.grad = flat[o:o + p.numel()].view_as(p)
 
-    # ---- the update ---------------------------------------------------------------------------
-    def _build_table(self, items):
-        rows = []
-        for p, g, m, v in items:
+    # ---- tracking -------------------------------------------------------------------------------
+    @contextlib.contextmanager
+    def track(self, expect):
+        """expect: {owner module: number of backward passes that will produce its weight gradients}."""
+        ps = self._params()
+        if not (self.overlap and self._flat_grads and ps and ps[0].is_cuda and self._owners):
+            yield None
+            return
+        from . import plan
+        self.flat_grad()
+        tr = _Tracker(self, expect)
+        plan._TRACKERS.append(tr)
+        try:
+            yield tr
+        finally:
+            plan._TRACKERS.remove(tr)
+        tr.finish()
+
+    # ---- the update -----------------------------------------------------------------------------
+    def _stream(self, dev):
+        if self._side is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+        return self._side
+
+    def _state_for(self, p):
+        st = self.state[p]
+        if len(st) == 0:
+            if self._m is None or self._m.device != self._flat.device:
+                self._m = torch.zeros_like(self._flat)
+                self._v = torch.zeros_like(self._flat)
+            st["step"] = torch.tensor(0.0, dtype=torch.float32)
+            o = self._offsets.get(id(p))
+            if o is not None and p.is_contiguous():
+                st["exp_avg"] = self._m[o:o + p.numel()].view_as(p)
+                st["exp_avg_sq"] = self._v[o:o + p.numel()].view_as(p)
+            else:
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        return st
+
+    def _table(self, b, wire):
+        rows, key = [], []
+        for p in b.params:
+            st = self._state_for(p)
+            o = self._offsets[id(p)]
+            if wire == "bf16":
+                g_ptr, g_item = self._wire.data_ptr() + 2 * o, 2
+            else:
+                g = p.grad
+                if g is None or not g.is_contiguous() or g.dtype != torch.float32:
+                    raise RuntimeError("FusedAdam: gradients must be contiguous fp32")
+                g_ptr, g_item = g.data_ptr(), 4
+            m, v = st["exp_avg"], st["exp_avg_sq"]
+            key.append((p.data_ptr(), g_ptr, m.data_ptr(), v.data_ptr()))
             n = p.numel()
-            for o in range(0, n, CHUNK):
-                rows.append((p.data_ptr() + 4 * o, g.data_ptr() + 4 * o, m.data_ptr() + 4 * o, v.data_ptr() + 4 * o,
-                             min(CHUNK, n - o)))
-        arr = (L.AdamChunk * len(rows))()
+            for c in range(0, n, CHUNK):
+                rows.append((p.data_ptr() + 4 * c, g_ptr + g_item * c, m.data_ptr() + 4 * c, v.data_ptr() + 4 * c, min(CHUNK, n - c)))
+        key = tuple(key)
+        cached = b.tables.get(wire)
+        if cached is not None and cached[0] == key:
+            return cached[1], cached[2]
+        arr = (L.AdamChunk * max(1, len(rows)))()
         for i, r in enumerate(rows):
             arr[i].p, arr[i].g, arr[i].m, arr[i].v, arr[i].numel = r
         host = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy())
-        return host.to(items[0][0].device), len(rows)
+        dev = host.to(b.params[0].device)
+        b.tables[wire] = (key, dev, len(rows))
+        return dev, len(rows)
+
+    def _process(self, b):
+        """The tail of one bucket: gradient accumulators -> .grad, (all-reduce), Adam, filter re-pack."""
+        from . import plan
+        if not b.params:
+            b.fired = True
+            return
+        dev = b.params[0].device
+        if not b.params[0].is_cuda:
+            raise RuntimeError("FusedAdam: CUDA parameters required (no CPU fallback)")
+        self.flat_grad()
+        cur = torch.cuda.current_stream(dev)
+        side = self._stream(dev) if self.overlap else None
+        if side is not None:
+            if b.events:
+                for ev in b.events.values():
+                    side.wait_event(ev)
+            else:
+                side.wait_stream(cur)
+            self._side_used = True
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            if b.holders:
+                plan.flush_grads(b.holders)
+            wire = "fp32"
+            if self.sync is not None and self.sync.world > 1:
+                wire = self.sync.reduce_bucket(self, b)
+            group = self.param_groups[0]
+            if len(self.param_groups) > 1:
+                raise RuntimeError("FusedAdam: one parameter group")
+            for k in ("weight_decay", "amsgrad", "maximize"):
+                if group.get(k):
+                    raise RuntimeError(f"FusedAdam: param_group option {k} is not supported")
+            beta1, beta2 = group["betas"]
+            table, nchunks = self._table(b, wire)
+            flags = 0
+            if not self._ticked:
+                self._sync_step_counter(dev)
+                flags |= L.ADAM_TICK
+                self._ticked = True
+            if wire == "bf16":
+                flags |= L.ADAM_GRAD_BF16
+            elif not self.keep_grads:
+                flags |= L.ADAM_ZERO_GRAD
+            ops.adam_multi(table, nchunks, self._dev_state, group["lr"], beta1, beta2, group["eps"], self.grad_scale, flags)
+            for p in b.params:        # the kernel wrote p behind autograd's back: invalidate packed copies
+                p._vcg_epoch = getattr(p, "_vcg_epoch", 0) + 1
+            if b.holders:
+                plan.refresh_holders(b.holders)
+        b.fired = True
+        b.events = {}
+
+    def _sync_step_counter(self, dev):
+        steps = [self._state_for(p)["step"] for p in self._params()]
+        before = int(steps[0].item())
+        if any(int(s.item()) != before for s in steps[1:]):
+            raise RuntimeError("FusedAdam: parameters of one optimiser must share the step count")
+        if self._dev_state is None or self._dev_state.device != dev:
+            self._dev_state = torch.zeros(4, dtype=torch.float32, device=dev)
+            self._dev_step = 0
+        if self._dev_step != before:          # first use / after load_state_dict: resync the device counter
+            self._dev_state[0:1].fill_(float(before))
+            self._dev_step = before
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         from . import plan
-        plan.flush_grads()          # no-op unless a backward was driven outside autograd
-        self.finish()               # a previous deferred step of this optimiser
-        if self.pre_step_hook is not None:
-            self.pre_step_hook(self)
-        if self.defer:
-            self._deferred = True
-            return loss
         ps = self._params()
-        if self.overlap and self.pre_step_hook is None and ps and ps[0].is_cuda:
-            if self._side is None:
-                self._side = torch.cuda.Stream(device=ps[0].device)
-            self._side.wait_stream(torch.cuda.current_stream(ps[0].device))
-            with torch.cuda.stream(self._side):
-                self._update()
-            self._side_pending = True
+        if not ps:
             return loss
-        self._update()
+        if not ps[0].is_cuda:
+            raise RuntimeError("FusedAdam: CUDA parameters required (no CPU fallback)")
+        if not self._flat_grads:
+            raise RuntimeError("FusedAdam: flat_grads=False is not supported by the fused update")
+        self.flat_grad()
+        pending = [b for b in self._buckets if not b.fired]
+        if any(b.holders is None for b in pending) or plan.has_pending():
+            plan.flush_grads()          # gradients produced outside a tracked backward (on the calling stream)
+        for b in pending:
+            self._process(b)
+        # host-side bookkeeping of one optimiser step
+        steps = [self.state[p]["step"] for p in ps if len(self.state[p])]
+        for s in steps:
+            s += 1
+        self._dev_step += 1
+        self._last = steps
+        self._ticked = False
+        for b in self._buckets:
+            b.fired = False
+        self._zeroed = not self.keep_grads      # consumed gradients were zeroed by the Adam / wire-cast kernels
         return loss
 
     @torch.no_grad()
     def finish(self):
-        """Complete a deferred step (join the gradient exchange, run the Adam kernel)."""
-        if self._side_pending:
-            self._side_pending = False
-            torch.cuda.current_stream(self._params()[0].device).wait_stream(self._side)
-        if self._deferred:
-            self._deferred = False
-            self._update()
+        """Join the side stream: afterwards the calling stream sees the updated weights and their packed copies."""
+        if self._side_used:
+            self._side_used = False
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
 
-    def _update(self):
-        if self.pre_update_hook is not None:
-            self.pre_update_hook(self)
-        for group in self.param_groups:
-            beta1, beta2 = group["betas"]
-            items, steps = [], []
-            for p in group["params"]:
-                if p.grad is None:
-                    continue
-                if not p.is_cuda:
-                    raise RuntimeError("FusedAdam: CUDA parameters required (no CPU fallback)")
-                st = self.state[p]
-                if len(st) == 0:
-                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                g = p.grad
-                if not g.is_contiguous() or g.dtype != torch.float32:
-                    raise RuntimeError("FusedAdam: gradients must be contiguous fp32")
-                items.append((p, g, st["exp_avg"], st["exp_avg_sq"]))
-                steps.append(st["step"])
-            if not items:
-                continue
-            key = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()) for p, g, m, v in items)
-            if key != self._table_key or len(self.param_groups) > 1:
-                self._table = self._build_table(items)
-                self._table_key = key
-            before = int(steps[0].item())
-            if any(int(s.item()) != before for s in steps[1:]):
-                raise RuntimeError("FusedAdam: parameters of one group must share the step count")
-            dev = items[0][0].device
-            if self._dev_state is None or self._dev_state.device != dev:
-                self._dev_state = torch.zeros(4, dtype=torch.float32, device=dev)
-                self._dev_step = 0
-            if self._dev_step != before:          # first use / after load_state_dict: resync the device counter
-                self._dev_state[0:1].fill_(float(before))
-            table, nchunks = self._table
-            ops.adam_multi(table, nchunks, self._dev_state, group["lr"], beta1, beta2, group["eps"], self.grad_scale)
-            self._dev_step = before + 1
-            self._last = (steps, [p for p, _, _, _ in items])
-            self._bump(steps, self._last[1])
+    def state_dict(self):
+        self.finish()
+        return super().state_dict()
 
-    @staticmethod
-    def _bump(steps, params):
-        for s in steps:
-            s += 1
-        for p in params:        # the kernel wrote p behind autograd's back: invalidate packed copies
-            p._vcg_epoch = getattr(p, "_vcg_epoch", 0) + 1
+    def load_state_dict(self, state_dict):
+        """torch's load replaces the state tensors; the loaded moments are copied back INTO the existing (flat-buffer)
+        tensors so that device tables -- possibly baked into a captured CUDA graph -- keep pointing at live memory."""
+        self.finish()
+        old = {p: dict(self.state[p]) for p in self._params() if len(self.state[p])}
+        super().load_state_dict(state_dict)
+        with torch.no_grad():
+            for p, o in old.items():
+                new = self.state[p]
+                for k in ("exp_avg", "exp_avg_sq"):
+                    if k in new and k in o and o[k].shape == new[k].shape and o[k].device == new[k].device:
+                        o[k].copy_(new[k])
+                        new[k] = o[k]
+        for b in self._buckets or []:
+            b.tables = {}
 
     def capture_rollback(self):
         """step() ran under CUDA-graph capture: its kernels were recorded, not executed; undo the host bump."""
         if self._last is not None:
-            for st in self._last[0]:
+            for st in self._last:
                 st -= 1
             self._dev_step -= 1
 
@@ -178,5 +395,8 @@ class FusedAdam(torch.optim.Adam):
         """A captured CUDA graph containing this optimiser's step was replayed: the device-side counter
         and the weights advanced; mirror that in the host-side state (state_dict 'step', cache epochs)."""
         if self._last is not None:
-            self._bump(*self._last)
+            for st in self._last:
+                st += 1
             self._dev_step += 1
+            for p in self._params():
+                p._vcg_epoch = getattr(p, "_vcg_epoch", 0) + 1

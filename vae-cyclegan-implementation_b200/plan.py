@@ -145,17 +145,28 @@ class PlanBuilder:
 
 # ----------------------------------------------------------------------------- parameter caches
 _TABLES = {}      # cached device-side job tables of the multi-tensor pack / unpack launches (keyed by pointers)
-_PENDING = []     # PackedConvs whose fp32 accumulators hold weight gradient not yet added to .grad
+_PENDING = {}     # id -> PackedConv whose fp32 accumulators hold weight gradient not yet added to .grad
 _FLUSH_QUEUED = [False]
+_TRACKERS = []    # optim._Tracker objects of the backward pass that is running (FusedAdam.track)
 
 
 def _cached_table(key, build):
+    """Device tables are never evicted: their addresses may be baked into a captured CUDA graph (graph.py).  A table
+    is a few KB and a training run creates a few dozen (one per bucket and layout)."""
     t = _TABLES.get(key)
     if t is None:
-        if len(_TABLES) > 256:
-            _TABLES.clear()
         t = _TABLES[key] = build()
     return t
+
+
+def has_pending():
+    return bool(_PENDING)
+
+
+def _mark_grad_written(param):
+    opt = getattr(param, "_vcg_opt", None)
+    if opt is not None:
+        opt.mark_dirty()
 
 
 class PackedConv:
@@ -200,7 +211,7 @@ class PackedConv:
     def mark_pending(self, bias):
         if not self.pending:
             self.pending = True
-            _PENDING.append(self)
+            _PENDING[id(self)] = self
         self.pending_bias = self.pending_bias or bias
 
 
@@ -229,18 +240,32 @@ def refresh_many(pcs, dtype):
         pc.key = pc._key(dtype)
 
 
-def flush_grads():
-    """Add every pending weight / bias gradient accumulator to its parameter's .grad (and re-zero the
-    accumulators): two multi-tensor launches for the whole model instead of one unpack per convolution."""
+def refresh_holders(holders, dtype=None):
+    """re-pack the stale filters of the given parameter holders (one launch)"""
+    pcs = [pc for h in holders for pc in h.__dict__.get("_vcg_packed", {}).values()]
+    if pcs:
+        refresh_many(pcs, dtype or _STATE["dtype"])
+
+
+def flush_grads(holders=None):
+    """Add pending weight / bias gradient accumulators to their parameters' .grad (and re-zero the accumulators):
+    two multi-tensor launches instead of one unpack per convolution.  holders=None: everything that is pending,
+    except what a running FusedAdam.track() will hand over bucket by bucket; else: only these holders."""
     if not _PENDING:
         return
-    pcs = list(_PENDING)
-    _PENDING.clear()
+    if holders is None:
+        pcs = [pc for pc in _PENDING.values() if not any(t.tracks(pc.holder) for t in _TRACKERS)]
+    else:
+        pcs = [pc for h in holders for pc in h.__dict__.get("_vcg_packed", {}).values() if pc.pending]
+    if not pcs:
+        return
     went, bent = [], []
     for pc in pcs:
+        _PENDING.pop(id(pc), None)
         w = pc.holder.weight
         if w.grad is None:
             w.grad = torch.zeros_like(w, memory_format=torch.contiguous_format)
+        _mark_grad_written(w)
         went.append((pc.spec, w.grad, pc.dw, None))
         if pc.pending_bias:
             b = pc.holder.bias
@@ -505,6 +530,9 @@ class Plan:
                         h.bias.grad = db[:1].clone()
                     else:
                         h.bias.grad.add_(db[:1])
+                    _mark_grad_written(h.weight_orig)
+                    for t in _TRACKERS:
+                        t.contributed(h)
                 dense.setdefault(node.inp.id, []).append(dx)
             elif isinstance(node, ReparamNode):
                 srcs = sources(node.z)
@@ -565,6 +593,12 @@ class Plan:
                     # gather of this gradient (it can feed two activations through a residual) reads one position
                     ops.fold_halo_(g, node.mode, node.pad, node.inp.h, node.inp.w, node.inp.c)
                     dxp[node] = g
+                if want_w:
+                    # FusedAdam.track: when this was the bucket's last contribution, its tail (unpack, all-reduce, Adam,
+                    # RE-PACK of the filters) starts on the side stream behind the event recorded here -- i.e. behind
+                    # this layer's weight-gradient AND data-gradient GEMM, the last readers of the packed filter
+                    for t in _TRACKERS:
+                        t.contributed(holder)
         if not defer_flush:
             flush_grads()
         res = []
