@@ -57,6 +57,11 @@ def parse():
     ap.add_argument("--gpu-reference", type=int, default=-1,
                     help="time the unmodified reference through stock PyTorch on this GPU (informational): 1 on, 0 off, "
                          "-1 auto (on for the single-GPU run)")
+    ap.add_argument("--overlap", type=int, default=-1,
+                    help="gradient-bucket tails (unpack, all-reduce, Adam, re-pack) on the optimisers' side streams behind the "
+                         "backward pass: 1 on, 0 off (same launches on the calling stream at step()), -1 library default")
+    ap.add_argument("--unfolded-max-hw", type=int, default=-1,
+                    help="plan.set_unfolded_max_hw: planes up to this many pixels skip the fold_halo launch (-1: library default)")
     ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32"], help="gradient all-reduce element type")
     ap.add_argument("--profile", type=int, default=1, help="1: external CUDA events around every launch inside the captured graph")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (vcg_b200.graph.GraphedStep)")
@@ -230,6 +235,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     lib.load()
     plan.set_precision(args.precision)
+    if args.unfolded_max_hw >= 0:
+        plan.set_unfolded_max_hw(args.unfolded_max_hw)
     from vcg_b200 import lanes
     if args.global_batch % world:
         raise SystemExit("global batch must be divisible by the number of GPUs")
@@ -244,6 +251,9 @@ def run_ours(args):
     model.configure_optimizers(lr=2e-4)
     model.configure_loss(lambda_kl=1e-5, lambda_gan=1.0, lambda_identity=5.0, lambda_cycle=10.0, lambda_recon=1.0)
     model.train()
+    if args.overlap >= 0:
+        for o in (model.optimizer_G, model.optimizer_D):
+            o.overlap = bool(args.overlap)
     sync = None
     if world > 1:
         vdist.broadcast_state(model)
@@ -385,7 +395,7 @@ def run_ours(args):
                                "256x256 training step, global batch %d, per-GPU batch %d" % (args.global_batch, per),
                    "global_batch": args.global_batch, "parallelism": f"dp{world}", "latent_dim": 64,
                    "l2": "working set (weights 276 MB bf16 + >10 GB activations per step) exceeds the 126 MB L2; no flush needed",
-                   "dead_passes_skipped": True, "cuda_graph": bool(args.graph), "lanes": use_lanes,
+                   "dead_passes_skipped": True, "cuda_graph": bool(args.graph), "lanes": use_lanes, "bucket_overlap": bool(model.optimizer_G.overlap),
                    "gradient_wire": (args.wire if world > 1 else None),
                    "wire_bytes_per_step_per_rank": (sum(o.flat_grad().numel() for o in (model.optimizer_G, model.optimizer_D)) *
                                                     (2 if args.wire == "bf16" else 4) if world > 1 else 0)},

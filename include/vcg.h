@@ -95,7 +95,8 @@ typedef struct vcg_conv_desc {
   int32_t out_c;      /* physical channels per output pixel */
   int32_t act;        /* VCG_ACT_* applied after bias, before stats */
   int32_t stats;      /* !=0: accumulate per-(n,cout) sum / sum-of-squares of the stored values */
-  int32_t flat;       /* !=0: tile the output in flattened input-pitch order (data-gradient); 2: the caller also
+  int32_t flat;       /* vcg_conv_wgrad: VCG_WGRAD_ALLOW_SIMT or 0.  vcg_conv_fwd:
+                         !=0: tile the output in flattened input-pitch order (data-gradient); 2: the caller also
                          guarantees that the outer (kh-1, kw-1) border of x is zero, so taps that only see the
                          border may be skipped (interior + ring schedule of conv_tc2.cu) */
   int32_t out_f32;    /* !=0: store y as fp32 even when dtype is VCG_BF16 (final image layer) */
@@ -108,6 +109,9 @@ typedef struct vcg_conv_desc {
 VCG_API int vcg_conv_fwd(const vcg_conv_desc* d, const void* x, const void* w, const float* bias,
                  void* y, float* stats, void* stream);
 
+/* desc->flat bit for vcg_conv_wgrad: maps that no tensor-core kernel can tile (below 8x8, i.e. inputs smaller than
+ * 256x256) may run on the ~50x slower SIMT kernel; without the bit such a shape is VCG_E_UNSUPPORTED.          */
+enum { VCG_WGRAD_ALLOW_SIMT = 4 };
 /* dw[co,kh,j] += sum_{n,h,w} dy[n,h+kh-1.., ...] ...: weight gradient, fp32 packed layout
  * [cout_pad,kh,kwc_pad], ACCUMULATED (split-K reductions use red.global.add).
  * x: the forward input [n,hp,wp,c]; dy: [n, ho+2*dy_halo, wo+2*dy_halo, dy_c] zero-haloed.      */
@@ -234,7 +238,14 @@ VCG_API int vcg_dhead_fwd(int32_t dtype, const void* x /*[n,k] NHWC-flattened*/,
 /* dx[n,:] = gs[n]*w/||w||; dw += (G - (G.w_hat) w_hat)/||w|| with G = sum_n gs[n] x[n]; dbias += sum gs */
 VCG_API int vcg_dhead_bwd(int32_t dtype, const void* x, const float* w_khwc, const float* wnorm2,
                   const float* gscore, int32_t n, int32_t k, void* dx, float* dw, float* dbias,
-                  float* scratch /*[k+1]*/, void* stream);
+                  float* scratch /*[k+1]*/, int32_t dw_c /*0: dw in (h,w,c) order; >0: OIHW gradient of [1,dw_c,kh,kw]*/,
+                  void* stream);
+/* One launch per discriminator and step: the power iteration every training forward of the reference runs
+ * (torch/nn/utils/spectral_norm.py:92-114: v = normalize(W^T u), u = normalize(W v), in place, when do_iter),
+ * the (h, w, c)-ordered filter copy the two calls above read, and aux = {sigma = u . (W v), |W|} (eval mode divides by
+ * the sigma of the stale u, v: spectral_norm.py:125-130).  w_oihw: [1, c, kh, kw] fp32, hw = kh*kw.           */
+VCG_API int vcg_dhead_prepare(const float* w_oihw, int32_t c, int32_t hw, float* u, float* v, float* w_hwc /*or NULL*/,
+                      float* aux /*[2] or NULL*/, double* scratch /*[3], caller-owned*/, int32_t do_iter, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Multi-tensor Adam (torch/optim/adam.py:457-547 as called from Networks.py:312,894,1032-1033,

@@ -28,6 +28,26 @@ def _worker(rank, world, port, q):
     sync.reduce(flat)
     sync.wait()
     ok = torch.equal(flat, torch.arange(2500, dtype=torch.float32) * 3)
+    # the per-bucket form optim.FusedAdam calls on its side stream: only [lo, hi) of the flat buffer is exchanged
+    # (fp32 wire on CPU tensors; the bf16 wire needs the CUDA cast kernel and is covered by tools/dp_check.py)
+    class _Opt:
+        keep_grads = True
+
+        def __init__(self, t):
+            self.t = t
+
+        def flat_grad(self):
+            return self.t
+
+    class _Bucket:
+        lo, hi = 100, 2300
+
+    flat2 = torch.arange(2500, dtype=torch.float32) * (rank + 1)
+    sync2 = vdist.GradSync(bucket_bytes=4096, wire="bf16")          # falls back to fp32 for non-CUDA buffers
+    assert sync2.reduce_bucket(_Opt(flat2), _Bucket()) == "fp32"
+    expect = torch.arange(2500, dtype=torch.float32) * (rank + 1)
+    expect[100:2300] = torch.arange(100, 2300, dtype=torch.float32) * 3
+    ok = ok and torch.equal(flat2, expect) and sync2.bytes_sent == 4 * 2200
     # mean over ranks of shard gradients == global-batch gradient for a mean loss
     w_ = torch.ones(3, requires_grad=True)
     (mine.mean(dim=(0, 2, 3)) * w_).sum().backward()

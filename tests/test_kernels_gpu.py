@@ -210,12 +210,12 @@ def test_conv_layer_fwd_bwd(K, prec, case):
     (r2 * q(gy, dt).double()).sum().backward()
     assert_close(got_dx, x2.grad, 1e-5 if prec == "fp32" else 6e-3, f"conv_dgrad {name}", "nchw")
     dw = torch.zeros(spec.packed_shape(False), dtype=torch.float32, device="cuda")
-    ops.conv_wgrad(spec, xp, dyp, dw)
+    ops.conv_wgrad(spec, xp, dyp, dw, allow_simt=True)      # odd-width test maps have no tensor-core wgrad kernel
     gw = torch.empty(co, ci_ref, k, k, dtype=torch.float32, device="cuda")
     ops.wunpack_grad(spec, dw, gw)
     assert_close(gw, w2.grad, 1e-5 if prec == "fp32" else 5e-3, f"conv_wgrad {name}", "oihw")
     # accumulate semantics
-    ops.conv_wgrad(spec, xp, dyp, dw)
+    ops.conv_wgrad(spec, xp, dyp, dw, allow_simt=True)
     ops.wunpack_grad(spec, dw, gw)
     assert_close(gw, 2 * w2.grad, 1e-5 if prec == "fp32" else 5e-3, f"conv_wgrad accumulate {name}", "oihw")
 
@@ -359,6 +359,41 @@ def test_dhead(K, prec):
     assert_close(nchw(dx.float()), x.grad, 1e-5 if prec == "fp32" else 6e-3, "dhead dx", "nchw")
     assert_close(dw.view(h, w, c).permute(2, 0, 1), wt.grad[0], 2e-5 if prec == "fp32" else 1e-3, "dhead dw", "chw")
     assert abs(float(db) - float(gs.sum())) < 1e-5
+    # the same gradient written straight into an OIHW tensor (the .grad view of the flat buffer), accumulating
+    g_oihw, db2 = torch.zeros(1, c, h, w, device="cuda"), torch.zeros(1, device="cuda")
+    for _ in range(2):
+        ops.dhead_bwd(xb, w_khwc, wn2, gs, dx, g_oihw, db2, scratch, dw_c=c)
+    assert_close(g_oihw[0], 2 * wt.grad[0], 2e-5 if prec == "fp32" else 1e-3, "dhead dw (OIHW, accumulated)", "chw")
+    assert abs(float(db2) - 2 * float(gs.sum())) < 1e-5
+
+
+def test_dhead_prepare_power_iteration(K):
+    """vcg_dhead_prepare == one power iteration of torch's spectral_norm on a 1 x K matrix (spectral_norm.py:92-114),
+    the (h, w, c) filter copy and {sigma, |W|}; without do_iter: sigma of the STALE u, v (eval mode, :125-130)."""
+    ops, L = K
+    c, h, w = 512, 16, 16
+    wt = rnd(1, c, h, w, seed=51, scale=0.0867)
+    g = torch.Generator().manual_seed(52)
+    u0 = F.normalize(torch.randn(1, generator=g), dim=0, eps=1e-12).cuda()
+    v0 = F.normalize(torch.randn(c * h * w, generator=g), dim=0, eps=1e-12).cuda()
+    wm = wt.reshape(1, -1)
+    v_ref = F.normalize(torch.mv(wm.t(), u0), dim=0, eps=1e-12)
+    u_ref = F.normalize(torch.mv(wm, v_ref), dim=0, eps=1e-12)
+    u, v = u0.clone(), v0.clone()
+    w_hwc, aux = torch.empty(c * h * w, device="cuda"), torch.empty(2, device="cuda")
+    ops.dhead_prepare(wt, u, v, w_hwc, aux, True)
+    assert torch.equal(u, u_ref) and rel_l2(v, v_ref) < 1e-6
+    assert torch.equal(w_hwc, wt[0].permute(1, 2, 0).contiguous().view(-1))
+    assert abs(float(aux[0]) - float(torch.dot(u_ref, torch.mv(wm, v_ref)))) < 1e-5 * float(wt.norm())
+    assert abs(float(aux[1]) - float(wt.norm())) < 1e-5 * float(wt.norm())
+    # idempotent: a second iteration on the result reproduces the same bits
+    u2, v2 = u.clone(), v.clone()
+    ops.dhead_prepare(wt, u2, v2, None, None, True)
+    assert torch.equal(u2, u) and torch.equal(v2, v)
+    # eval mode: stale u, v against a perturbed weight
+    w2 = wt * 1.01 + 0.001
+    ops.dhead_prepare(w2, u, v, None, aux, False)
+    assert abs(float(aux[0]) - float(torch.dot(u, torch.mv(w2.reshape(1, -1), v)))) < 1e-5 * float(w2.norm())
 
 
 def test_adam_multi(K):

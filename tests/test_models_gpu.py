@@ -395,47 +395,70 @@ def test_double_models_train_and_convert(env, name):
 @pytest.mark.parametrize("arch", ["cyclevaegan", "vaegan", "cyclevae"])
 def test_lanes_and_bucket_overlap_match_the_serial_step(env, arch):
     """The concurrent schedule (two lanes, gradient buckets applied on the optimiser's side stream while the backward
-    pass still runs; lanes.py, optim.FusedAdam.track) must compute what the serial schedule computes: three steps in
-    fp32 mode with identical noise, metrics to 1e-4 and weights to a fraction of one Adam step."""
+    pass still runs; lanes.py, optim.FusedAdam.track) must compute what the serial schedule computes.  fp32 mode,
+    identical noise.  Decisive part: the FIRST step taken from identical weights -- metrics and every gradient tensor
+    equal up to the atomics' summation order (a bucket handed over before its last contribution, or a filter
+    re-packed under a running data-gradient GEMM, would show here).  Two more steps follow with chaos-level bounds:
+    after an Adam step (sign-like at the start) rounding-level differences move generator-side losses by ~2e-4 -- the
+    reference's own fp32 and fp64 runs differ by 2.3e-4 on loss_cycle after one step (tests/golden/noise_floor.json)."""
     N, plan, rp = env
     from vcg_b200 import lanes
     plan.set_precision("fp32")
     N.set_eps_source(cpu_eps_source)
     batch = {k: v.cuda() for k, v in rp.synthetic_batch(1).items()}
+    kw = {"paired": False} if arch.startswith("cycle") else {}
 
     def run(concurrent):
         prev = lanes.set_enabled(concurrent)
         try:
             torch.manual_seed(1234)
-            kw = {"paired": False} if arch.startswith("cycle") else {}
             m = getattr(N, CLS[arch])(**kw).cuda()
             m.configure_optimizers(lr=2e-4)
-            for o in (getattr(m, n, None) for n in ("optimizer", "optimizer_G", "optimizer_D")):
-                if o is not None:
-                    o.overlap = concurrent
+            opts = [o for o in (getattr(m, n, None) for n in ("optimizer", "optimizer_G", "optimizer_D")) if o is not None]
+            for o in opts:
+                o.overlap = concurrent
+                o.keep_grads = True
             m.configure_loss(**rp.DEFAULT_LAMBDAS)
             m.train()
-            out = []
+            torch.manual_seed(99)
+            with torch.no_grad():                   # plans and packed filters exist afterwards: the first step is "warm"
+                m(batch["x"], batch["y"])
+            out, grads = [], None
             for s in range(3):
                 torch.manual_seed(100 + s)
                 out.append(m.training_step(batch))
-            return out, {k: v.detach().clone() for k, v in m.state_dict().items()}
+                if s == 0:
+                    for o in opts:
+                        o.finish()
+                    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+            return out, grads, {k: v.detach().clone() for k, v in m.state_dict().items()}
         finally:
             lanes.set_enabled(prev)
 
-    ms, ws = run(False)
-    mc, wc = run(True)
-    for a, b in zip(ms, mc):
-        for k in a:
-            assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(a[k])), (arch, k, a[k], b[k])
+    ms, gs, ws = run(False)
+    mc, gc, wc = run(True)
+    for k in ms[0]:
+        assert abs(ms[0][k] - mc[0][k]) <= 1e-5 * max(1.0, abs(ms[0][k])), (arch, "step 0", k, ms[0][k], mc[0][k])
+    dead = ("encoder.model.0.conv.bias", "encoder.model.5.conv2.bias", "decoder.model.0.conv2.bias",
+            "model.1.conv.bias", "model.2.conv.bias", "model.3.conv.bias")
+    for k in gs:
+        if k.endswith(dead) and ("encoder" in k or "decoder" in k or k.split(".")[0].startswith("D")):
+            continue        # bias in front of an InstanceNorm: mathematically zero gradient, pure summation-order noise
+        scale = float(gs[k].norm())
+        assert float((gs[k] - gc[k]).norm()) <= 2e-4 * scale + 1e-6, (arch, "gradient", k, rel_l2(gc[k], gs[k]))
+    for s in (1, 2):
+        for k in ms[s]:
+            disc = "gan" in k or k.startswith(("D_loss", "d_", "total_loss"))
+            tol = 0.1 if disc else 2e-3
+            assert abs(ms[s][k] - mc[s][k]) <= tol * max(1.0, abs(ms[s][k])), (arch, s, k, ms[s][k], mc[s][k])
     torch.manual_seed(1234)
-    w0 = getattr(N, CLS[arch])(**({"paired": False} if arch.startswith("cycle") else {})).state_dict()
+    w0 = getattr(N, CLS[arch])(**kw).state_dict()
     for k in ws:
         if ws[k].dim() < 2:
             continue
         moved = rel_l2(ws[k].cpu(), w0[k])
         assert moved > 0, k
-        assert rel_l2(wc[k], ws[k]) < 0.1 * moved + 1e-7, (arch, k, rel_l2(wc[k], ws[k]), moved)
+        assert rel_l2(wc[k], ws[k]) < 0.3 * moved + 1e-7, (arch, k, rel_l2(wc[k], ws[k]), moved)
     N.set_eps_source(None)
     plan.set_precision("bf16")
 
@@ -495,7 +518,10 @@ def test_train_epoch_keeps_the_reference_random_stream(env):
     def fresh():
         torch.manual_seed(21)
         m = N.VAEGAN().cuda()
-        m.configure_optimizers(lr=2e-4)
+        # lr = 0: the steps run in full (forward, both backward sweeps, Adam launches) but the weights stay put, so the
+        # two loops can be compared tightly -- after real Adam steps (sign-like at the start) two runs of the SAME
+        # loop already differ by tens of percent in the generated image (summation-order noise flips update signs)
+        m.configure_optimizers(lr=0.0)
         m.configure_loss(**rp.DEFAULT_LAMBDAS)
         return m
 
@@ -517,11 +543,11 @@ def test_train_epoch_keeps_the_reference_random_stream(env):
     loss, comps, out_b, lx, ly = T.train_epoch(b_model, batches, torch.device("cuda"), argparse.Namespace(cuda_graph=False))
     rng_b = torch.cuda.get_rng_state()
     assert torch.equal(rng_a, rng_b), "train_epoch consumed a different amount of CUDA randomness than the reference's loop"
-    assert set(comps) == set(sums) and abs(loss - sums["G_loss"] / 3) <= 2e-3 * abs(loss)
-    for k in ("loss_trans", "loss_kl", "loss_identity"):
-        assert abs(comps[k] - sums[k] / 3) <= 2e-3 * abs(comps[k]) + 1e-6, (k, comps[k], sums[k] / 3)
+    assert set(comps) == set(sums) and abs(loss - sums["G_loss"] / 3) <= 1e-4 * abs(loss)
+    for k in comps:
+        assert abs(comps[k] - sums[k] / 3) <= 1e-4 * abs(comps[k]) + 1e-6, (k, comps[k], sums[k] / 3)
     assert out_b.shape == (1, 3, 256, 256) and torch.equal(lx.cpu(), batches[-1]["x"])
-    assert rel_l2(out_b, out_a) < 2e-2          # same noise, weights equal up to the atomics' order after 3 Adam steps
+    assert rel_l2(out_b, out_a) < 1e-4          # same weights, same noise: the display forward of the last batch
     # validate(): eval mode, the reference's 6-tuple
     vloss, vcomps, gx, fy, vx, vy = T.validate(b_model, batches[:2], torch.device("cuda"))
     assert not b_model.training and gx.shape == (1, 3, 256, 256) and fy is None and "G_loss" in vcomps and vloss == vloss

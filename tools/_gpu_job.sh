@@ -1,9 +1,9 @@
-# round-2 GPU job: full GPU suite, then the per-GPU-batch sweep of the step (lanes on / off), event overhead check
-python -m pytest tests -m gpu -q -x --deselect tests/test_baseline_configs_gpu.py > gpurun_out/r2_t3.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_t3.log
-tail -4 gpurun_out/r2_t3.log
-python -m pytest tests/test_baseline_configs_gpu.py -m gpu -q -s > gpurun_out/r2_t3_baseline.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_t3_baseline.log
-grep -E "^\[config|passed|failed|Error|assert" gpurun_out/r2_t3_baseline.log | cut -c1-400 | tail -30
-for gb in 64 32 16 8; do for ln in 0 1; do python bench.py --global-batch $gb --lanes $ln --steps 10 --warmup 3 --no-cpu-baseline --gpu-reference 0 > gpurun_out/r2_b3_gb${gb}_l${ln}.log 2>&1; echo "gb$gb lanes$ln $(tail -1 gpurun_out/r2_b3_gb${gb}_l${ln}.log | cut -c90-200)"; done; done
-python bench.py --global-batch 64 --profile 0 --steps 10 --warmup 3 --no-cpu-baseline --gpu-reference 0 > gpurun_out/r2_b3_gb64_noprof.log 2>&1; echo "gb64 noprofile $(tail -1 gpurun_out/r2_b3_gb64_noprof.log | cut -c90-200)"
-python bench.py --global-batch 8 --profile 0 --steps 10 --warmup 3 --no-cpu-baseline --gpu-reference 0 > gpurun_out/r2_b3_gb8_noprof.log 2>&1; echo "gb8 noprofile $(tail -1 gpurun_out/r2_b3_gb8_noprof.log | cut -c90-200)"
-VCG_BENCH_LAYERS=gpurun_out/r2_layers_b8_graph.txt python bench.py --global-batch 8 --lanes 0 --steps 5 --warmup 3 --no-cpu-baseline --gpu-reference 0 > gpurun_out/r2_b3_gb8_layers.log 2>&1
+# round-2 GPU job 7: suite, step at batch 64 / 8 after the epilogue-register and dhead_prepare fixes, unfolded-halo A/B
+python -m pytest tests -m gpu -q > gpurun_out/r2_t7.log 2>&1; echo "suite rc=$?"
+grep -E "^FAILED|^ERROR|passed|failed" gpurun_out/r2_t7.log | cut -c1-200 | tail -12
+grep -E "^E  " gpurun_out/r2_t7.log | cut -c1-250 | head -12
+grep -E "\[config|\[white" gpurun_out/r2_t7.log | cut -c1-300
+B="--steps 10 --warmup 3 --no-cpu-baseline --gpu-reference 0 --profile 0"
+for gb in 64 8; do for uf in 0 1024 4096; do python bench.py --global-batch $gb --unfolded-max-hw $uf $B > gpurun_out/r2_b7_gb${gb}_uf${uf}.log 2>&1; echo "gb$gb unfolded$uf $(tail -1 gpurun_out/r2_b7_gb${gb}_uf${uf}.log | cut -c90-200)"; done; done
+python bench.py --global-batch 16 $B > gpurun_out/r2_b7_gb16.log 2>&1; echo "gb16 $(tail -1 gpurun_out/r2_b7_gb16.log | cut -c90-200)"
+python bench.py --global-batch 32 $B > gpurun_out/r2_b7_gb32.log 2>&1; echo "gb32 $(tail -1 gpurun_out/r2_b7_gb32.log | cut -c90-200)"

@@ -75,20 +75,12 @@ class SpectralConvParams(nn.Module):
     @torch.no_grad()
     def power_iteration(self):
         """One power iteration as every training forward of the reference does
-        (torch/nn/utils/spectral_norm.py:92-114).  With a 1 x K matrix it converges in one step:
-        v = +-W/|W|, u = +-1, so sigma = |W| and the kernel's unit-vector form is exact.  u is a normalised
-        1-vector, i.e. exactly +-1, so repeating the iteration on unchanged W, u, v reproduces the same bits:
-        the reference's further iterations within one step (one per discriminator call, Networks.py:1916-1919,
-        2032-2035) are skipped."""
-        w = self.weight_orig
-        key = (w._version, getattr(w, "_vcg_epoch", 0), w.data_ptr(), self.weight_u._version, self.weight_v._version)
-        if self.__dict__.get("_vcg_pi_key") == key:
-            return
-        wm = w.reshape(w.shape[0], -1)
-        self.weight_v.copy_(F.normalize(torch.mv(wm.t(), self.weight_u), dim=0, eps=1e-12))
-        self.weight_u.copy_(F.normalize(torch.mv(wm, self.weight_v), dim=0, eps=1e-12))
-        self.__dict__["_vcg_pi_key"] = (w._version, getattr(w, "_vcg_epoch", 0), w.data_ptr(), self.weight_u._version,
-                                        self.weight_v._version)
+        (torch/nn/utils/spectral_norm.py:92-114), by one kernel launch (csrc/losses.cu, vcg_dhead_prepare).  With a
+        1 x K matrix it converges in one step: v = +-W/|W|, u = +-1, so sigma = |W| and the head kernels' unit-vector
+        form is exact.  u is a normalised 1-vector, i.e. exactly +-1, so repeating the iteration on unchanged W, u, v
+        reproduces the same bits: the reference's further iterations within one step (one per discriminator call,
+        Networks.py:1916-1919, 2032-2035) are skipped (plan.head_state keeps the key)."""
+        _plan.head_state(self, iterate=True)
 
 
 def _kaiming_init(module, nonlinearity="relu", a=0.0):
@@ -140,6 +132,9 @@ class CaSb(_PlanModule):
         mode = _L.MODE_PLAIN if self.stride == 1 else _L.MODE_PAD_S2D
         if self.use_norm:
             return b.conv(self.conv, a, mode, self.padding, _L.ACT_NONE, True, self.act)
+        if self.act in (_L.ACT_TANH, _L.ACT_SIGMOID):
+            # not fused in the conv epilogues (no shipped network uses them): applied by the consumer's transform pass
+            return b.conv(self.conv, a, mode, self.padding, _L.ACT_NONE, False, self.act)
         return b.conv(self.conv, a, mode, self.padding, self.act, False, _L.ACT_NONE)
 
 
@@ -282,10 +277,10 @@ class Discriminator(_PlanModule):
             head.power_iteration()
         out = self._run("fwd", [x], lambda b, ins: self.emit(b, ins[0]))[0]
         if not self.training:
-            # eval: sigma from the stale u, v of the last training forward (spectral_norm.py:125-130)
-            w = head.weight_orig.detach()
-            sigma = torch.dot(head.weight_u, torch.mv(w.reshape(w.shape[0], -1), head.weight_v))
-            out = head.bias.detach() + (out - head.bias.detach()) * (w.norm() / sigma)
+            # eval: sigma from the stale u, v of the last training forward (spectral_norm.py:125-130); the head kernel
+            # divided by |W|: rescale by |W| / sigma (both from vcg_dhead_prepare)
+            aux = _plan.head_state(head)["aux"]
+            out = head.bias.detach() + (out - head.bias.detach()) * (aux[1] / aux[0])
         return out
 
 
@@ -346,9 +341,7 @@ class _Composite(_PlanModule):
         for m in mods:
             if isinstance(m, SpectralConvParams):
                 if m.weight_orig.is_cuda:
-                    _plan.head_weight(m)
-                    if self.training:
-                        m.power_iteration()
+                    _plan.head_state(m, iterate=self.training)
                 continue
             cache = m.__dict__.get("_vcg_packed")
             if not cache:

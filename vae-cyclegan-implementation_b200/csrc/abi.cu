@@ -105,21 +105,18 @@ bool vcg_wgrad_thin_supported(const vcg_conv_desc*);
 int vcg_conv_wgrad_fold(const vcg_conv_desc*, const void*, const void*, int, int, float*, cudaStream_t);
 bool vcg_wgrad_fold_supported(const vcg_conv_desc*, int, int);
 
-static bool force_simt() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("VCG_FORCE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
 
 extern "C" int vcg_conv_fwd(const vcg_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                             float* stats, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VCG_REQUIRE(d && x && w && y, VCG_E_INVALID, "conv_fwd: null argument");
   VCG_REQUIRE(d->dtype == VCG_F32 || d->dtype == VCG_BF16, VCG_E_UNSUPPORTED, "conv_fwd: dtype %d", d->dtype);
-  if (d->dtype == VCG_F32 || force_simt()) {
+  if (d->dtype == VCG_F32) {
     VCG_REQUIRE(!(d->stats && stats), VCG_E_UNSUPPORTED, "conv_fwd: the SIMT path has no fused statistics; use vcg_in_stats");
     return vcg_conv_fwd_simt(d, d->dtype, x, w, bias, y, d->out_f32, stream);
   }
+  VCG_REQUIRE(d->act <= VCG_ACT_LEAKY, VCG_E_UNSUPPORTED,
+              "conv_fwd: activation %d is not fused in the tensor-core epilogues (Tanh / Sigmoid run in vcg_xform_fwd)", d->act);
   return vcg_conv_fwd_tc(d, x, w, bias, y, stats, d->out_f32, stream);
 }
 
@@ -133,13 +130,20 @@ extern "C" int vcg_conv_wgrad(const vcg_conv_desc* d, const void* x, const void*
   const int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
   const bool tileable = wo >= 64 ? (wo % 64 == 0) : (64 % wo == 0 && ho % (64 / wo) == 0);
   // the two 7x7 image-side layers (64->3 and 3->64): horizontal taps folded into N, row pairs stacked into M
-  static const bool no_wfold = getenv("VCG_NO_WFOLD") && getenv("VCG_NO_WFOLD")[0] == '1';      // A/B timing switch
-  if (d->dtype == VCG_BF16 && !force_simt() && !no_wfold && vcg_wgrad_fold_supported(d, dy_halo, dy_c))
+  if (d->dtype == VCG_BF16 && vcg_wgrad_fold_supported(d, dy_halo, dy_c))
     return vcg_conv_wgrad_fold(d, x, dy, dy_halo, dy_c, dw, stream);
   // bf16 mode, cout <= 4 (the 64->3 output convolution) on maps the fold kernel does not take: HMMA kernel
-  if (d->dtype == VCG_BF16 && !force_simt() && vcg_wgrad_thin_supported(d)) return vcg_conv_wgrad_thin(d, x, dy, dy_halo, dy_c, dw, stream);
-  if (d->dtype == VCG_F32 || force_simt() || d->cout < 16 || !tileable)
+  if (d->dtype == VCG_BF16 && vcg_wgrad_thin_supported(d)) return vcg_conv_wgrad_thin(d, x, dy, dy_halo, dy_c, dw, stream);
+  if (d->dtype == VCG_F32) return vcg_conv_wgrad_simt(d, d->dtype, x, dy, dy_halo, dy_c, dw, stream);
+  if (d->cout < 16 || !tileable) {
+    // no tensor-core kernel takes this shape.  The SIMT kernel is ~50x slower, so it runs only when the caller asked
+    // for it (VCG_WGRAD_ALLOW_SIMT in desc->flat: maps below 8x8, i.e. inputs smaller than the 256x256 the networks
+    // are built for); anything else is an error, not a silent cliff
+    VCG_REQUIRE(d->flat & VCG_WGRAD_ALLOW_SIMT, VCG_E_UNSUPPORTED,
+                "conv_wgrad: no tensor-core kernel for cout=%d on a %dx%d map (set VCG_WGRAD_ALLOW_SIMT to run the SIMT kernel)",
+                d->cout, ho, wo);
     return vcg_conv_wgrad_simt(d, d->dtype, x, dy, dy_halo, dy_c, dw, stream);
+  }
   // 256-channel-multiple outputs: CTA-pair kernel (256 x 256 tiles, half of the X tile per CTA)
   if (vcg_wgrad2_supported(d, dy_c)) return vcg_conv_wgrad_tc2(d, x, dy, dy_halo, dy_c, dw, stream);
   return vcg_conv_wgrad_tc(d, x, dy, dy_halo, dy_c, dw, stream);

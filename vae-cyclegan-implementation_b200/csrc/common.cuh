@@ -83,12 +83,19 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p,
   *reinterpret_cast<uint4*>(p) = r;
 }
 
+// the activations of every shipped network: ReLU / LeakyReLU(0.2) / identity (hot loops, conv epilogues)
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == VCG_ACT_RELU) return v > 0.f ? v : 0.f;
   if (act == VCG_ACT_LEAKY) return v > 0.f ? v : 0.2f * v;
+  return v;
+}
+// ... plus CaSb's Tanh / Sigmoid choices (Networks.py:63-71; no shipped network uses them).  Kept out of the conv
+// epilogues: inlining tanhf / expf into bias_act32 took conv_tc2_kernel from 128 to 162 registers.  They run in the
+// transform pass (vcg_xform_fwd) and in the SIMT parity kernels.
+__device__ __forceinline__ float act_apply_any(float v, int act) {
   if (act == VCG_ACT_TANH) return tanhf(v);
   if (act == VCG_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
-  return v;
+  return act_apply(v, act);
 }
 // derivative expressed through the activation OUTPUT o (ReLU/LeakyReLU keep the sign; tanh' = 1 - o^2, sigmoid' = o(1-o))
 __device__ __forceinline__ float act_grad(float o, int act) {
@@ -100,7 +107,7 @@ __device__ __forceinline__ float act_grad(float o, int act) {
 }
 // derivative expressed through the activation INPUT z (where the saved tensor is the pre-activation value)
 __device__ __forceinline__ float act_grad_in(float z, int act) {
-  if (act == VCG_ACT_TANH || act == VCG_ACT_SIGMOID) return act_grad(act_apply(z, act), act);
+  if (act == VCG_ACT_TANH || act == VCG_ACT_SIGMOID) return act_grad(act_apply_any(z, act), act);
   return act_grad(z, act);
 }
 // branch-free form for inner loops: slope = act_slope(act) once per kernel, then one compare + select per element
@@ -298,9 +305,6 @@ __device__ __forceinline__ void bias_act32(float (&v)[32], const float* __restri
   } else if (act == VCG_ACT_LEAKY) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
-  } else if (act == VCG_ACT_TANH || act == VCG_ACT_SIGMOID) {      // CaSb(activation="Tanh"/"Sigmoid"), Networks.py:63-71
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], act);
   }
   if (ncols < 32) {
 #pragma unroll

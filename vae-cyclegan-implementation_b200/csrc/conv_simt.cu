@@ -80,7 +80,7 @@ conv_fwd_simt_kernel(const T* __restrict__ x, const T* __restrict__ w, const flo
       if (co >= p.out_c) continue;
       // pad channels [cout, out_c) are written as zeros, like the tensor-core epilogue does
       float v = co < p.cout ? static_cast<float>(acc[i][j] + (bias ? static_cast<double>(bias[co]) : 0.0)) : 0.f;
-      v = act_apply(v, p.act);
+      v = act_apply_any(v, p.act);
       if (p.out_f32) reinterpret_cast<float*>(y)[pix * p.out_c + co] = v;
       else Elem<T>::st(reinterpret_cast<T*>(y) + pix * p.out_c + co, v);
     }

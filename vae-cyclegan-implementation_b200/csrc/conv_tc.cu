@@ -539,8 +539,7 @@ int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const 
   const int ho = d->hp - d->kh + 1, wo = d->wp - d->kw + 1;
   // thin outputs on wide maps (64->3 7x7, the data gradients of 3->64 7x7 and 32->64 3x3): horizontal taps folded
   // into N, input rows streamed once through a ring of TMEM accumulators (conv_tc_fold.cu)
-  static const bool no_fold = getenv("VCG_NO_FOLD") && getenv("VCG_NO_FOLD")[0] == '1';      // A/B timing switch
-  if (!no_fold && vcg_conv_fold_supported(d, d->stats && stats)) return vcg_conv_fwd_tc_fold(d, x, w, bias, y, out_f32, stream);
+  if (vcg_conv_fold_supported(d, d->stats && stats)) return vcg_conv_fwd_tc_fold(d, x, w, bias, y, out_f32, stream);
   if (vcg_conv2_supported(d, out_f32)) return vcg_conv_fwd_tc2(d, x, w, bias, y, stats, stream);
   VCG_REQUIRE(d->c % 8 == 0 && d->kwc_pad % 64 == 0 && d->cout_pad % 16 == 0 && d->out_c % 8 == 0,
               VCG_E_UNSUPPORTED, "conv_tc: unsupported channel geometry c=%d kwc_pad=%d cout_pad=%d cout=%d",
@@ -578,40 +577,26 @@ int vcg_conv_fwd_tc(const vcg_conv_desc* d, const void* x, const void* w, const 
   a.cout = d->cout; a.out_c = d->out_c; a.act = d->act; a.stats = (d->stats && stats) ? 1 : 0;
   a.out_f32 = out_f32;
   a.bias = bias; a.stats_acc = stats; a.out = y;
-  {
-    // timing experiment only (results are garbage): read both operands as MN-major to measure its smem cost
-    static const int exp_mn = (getenv("VCG_EXP_MN") && getenv("VCG_EXP_MN")[0] == '1') ? 1 : 0;
-    a.idesc = umma_idesc_bf16(128, bn, exp_mn, exp_mn);
-  }
+  a.idesc = umma_idesc_bf16(128, bn, 0, 0);
   // resident filter: one n-tile, many tiles per CTA, and the whole filter fits beside >= 4 A stages
-  static const bool no_bres = getenv("VCG_NO_BRES") && getenv("VCG_NO_BRES")[0] == '1';      // A/B timing switch
   const size_t filt_bytes = static_cast<size_t>(a.kblocks) * bn * 128;
-  a.bres = (!no_bres && ntn == 1 && a.num_tiles >= 4 * sms && filt_bytes + 4 * kAStageBytes + 3072 + 8192 + 40960 <= 227 * 1024) ? 1 : 0;
+  a.bres = (ntn == 1 && a.num_tiles >= 4 * sms && filt_bytes + 4 * kAStageBytes + 3072 + 8192 + 40960 <= 227 * 1024) ? 1 : 0;
   // staged epilogue: needs a 128 x BN output tile (+ row table + reduction slab) in shared memory
-  static const bool no_epi2 = getenv("VCG_NO_EPI2") && getenv("VCG_NO_EPI2")[0] == '1';      // A/B timing switch
   const int esz = out_f32 ? 4 : 2;
   // measured (tools/bench_conv.py, B=64): BN=128 layers gain (256->128 @128^2 forward 1020 -> 1178 TFLOP/s); BN=64 tiles
   // are bound by the MMA's shared-memory operand reads and the extra tile traffic costs 10 %, so they keep the
   // direct epilogue
-  a.epi2 = (!no_epi2 && bn == 128 && !out_f32 && static_cast<long long>(d->n) * ho * wo < (1LL << 31)) ? 1 : 0;
+  a.epi2 = (bn == 128 && !out_f32 && static_cast<long long>(d->n) * ho * wo < (1LL << 31)) ? 1 : 0;
   a.nacc = 2;
-  static const bool no_ssm = getenv("VCG_NO_STATS_SMEM") && getenv("VCG_NO_STATS_SMEM")[0] == '1';   // A/B timing switch
-  a.stats_smem = (!no_ssm && a.stats && !a.epi2 && a.kblocks <= 24) ? 1 : 0;   // measured: +13 % at 18 k-blocks, -3 % at 36
-  static const bool no_epi3 = getenv("VCG_NO_EPI3") && getenv("VCG_NO_EPI3")[0] == '1';      // A/B timing switch
-  static const bool no_tstore = getenv("VCG_NO_TSTORE") && getenv("VCG_NO_TSTORE")[0] == '1';  // A/B timing switch
-  a.epi3 = (!no_epi3 && !a.epi2 && !out_f32 && ntn == 1 && (bn == 64 || bn == 32)) ? 1 : 0;
-  a.tstore = (a.epi3 && !no_tstore && !a.flat && bn == 64 && d->cout == 64 && d->out_c == 64 && a.tw == 128 && a.th == 1) ? 1 : 0;
+  a.stats_smem = (a.stats && !a.epi2 && a.kblocks <= 24) ? 1 : 0;   // measured: +13 % at 18 k-blocks, -3 % at 36
+  a.epi3 = (!a.epi2 && !out_f32 && ntn == 1 && (bn == 64 || bn == 32)) ? 1 : 0;
+  a.tstore = (a.epi3 && !a.flat && bn == 64 && d->cout == 64 && d->out_c == 64 && a.tw == 128 && a.th == 1) ? 1 : 0;
   if (a.epi3) a.stats_smem = 0;
   const size_t epi_bytes = a.tstore ? 3 * 16384 : a.epi2 ? static_cast<size_t>(128) * bn * esz + 512 + 4096 : (a.stats_smem ? 8 * 32 * 36 * 4 : 0);
-  static const bool no_rowwin = getenv("VCG_NO_ROWWIN") && getenv("VCG_NO_ROWWIN")[0] == '1';      // A/B timing switch
-  a.rowwin = (!no_rowwin && a.bres && window && d->c == 8 && d->kwc_pad == 64 && a.tw == 128 && a.th == 1) ? 1 : 0;
+  a.rowwin = (a.bres && window && d->c == 8 && d->kwc_pad == 64 && a.tw == 128 && a.th == 1) ? 1 : 0;
   if (a.rowwin) a.a_tx_bytes = kRowWinPix * 16;
-  { static const int ex = getenv("VCG_EXP_EPI") ? atoi(getenv("VCG_EXP_EPI")) : 0; a.exp = ex; }
-  {
-    const char* e = getenv("VCG_EXP_SHIFT");
-    a.ashift = (e && !window && !a.rowwin && a.tw == 128 && a.th == 1) ? atoi(e) : 0;
-    if (a.ashift) a.a_tx_bytes = 17408;
-  }
+  a.exp = 0;        // timing experiments of round 1 (epilogue-only / row-shifted A descriptors), see DESIGN.md section 6
+  a.ashift = 0;
   const int a_stage = a.ashift ? 17408 : kAStageBytes;
   const int stage_bytes = a.rowwin ? kRowWinStage : (a.bres ? a_stage : a_stage + bn * 128);
   int stages = static_cast<int>((227 * 1024 - 3072 - 8192 - (a.bres ? filt_bytes : 0) - epi_bytes) / stage_bytes);

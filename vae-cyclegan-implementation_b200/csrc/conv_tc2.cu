@@ -494,8 +494,7 @@ double rounds_cost(int tiles256, int max_pairs, bool bn256) {
 }  // namespace
 
 bool vcg_conv2_supported(const vcg_conv_desc* d, int out_f32) {
-  static const bool off = getenv("VCG_TC2") && getenv("VCG_TC2")[0] == '0';        // A/B timing switch
-  if (off || out_f32) return false;
+  if (out_f32) return false;
   if (d->c % 64 != 0 || d->kwc_pad != d->kw * d->c) return false;
   // 128-channel-multiple outputs; 64 output channels only for data gradients (no statistics: the thin-N epilogue of
   // conv_tc.cu is the better forward path at N = 64)
@@ -512,9 +511,8 @@ int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const
   Conv2Args a{};
   // interior + ring data gradient: flat == 2 promises a zero halo of (kh - 1, kw - 1) around dY; 3 x 3 filters on maps
   // whose interior tiles exactly (16 x 16, 32 x 32, 64 x 64), no statistics
-  static const bool no_ring = getenv("VCG_NO_RING") && getenv("VCG_NO_RING")[0] == '1';        // A/B timing switch
   const int hi = ho - 2, wi = wo - 2;                       // interior = the forward layer's input map
-  a.ring = (!no_ring && d->flat == 2 && d->kh == 3 && d->kw == 3 && !(d->stats && stats) && (wi == 16 || wi == 32 || wi == 64) &&
+  a.ring = (d->flat == 2 && d->kh == 3 && d->kw == 3 && !(d->stats && stats) && (wi == 16 || wi == 32 || wi == 64) &&
             hi >= 8 && hi <= 128 && 128 % hi == 0 && hi % (128 / wi) == 0) ? 1 : 0;
   a.n_img = d->n; a.wp = d->wp;
   a.flat = d->flat ? 1 : 0; a.kh = d->kh; a.kw = d->kw;
@@ -555,8 +553,7 @@ int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const
   a.bias = bias; a.stats_acc = stats; a.out = y;
   a.idesc = umma_idesc_bf16(256, bn, 0, 0);
   a.idesc_half = umma_idesc_bf16(256, 128, 0, 0);
-  static const bool no_epi2 = getenv("VCG_NO_EPI2") && getenv("VCG_NO_EPI2")[0] == '1';      // A/B timing switch
-  a.epi2 = (!no_epi2 && bn == 128) ? 1 : 0;
+  a.epi2 = bn == 128 ? 1 : 0;
   const int epi_bytes = a.epi2 ? 128 * bn * 2 + 1024 + 4096 : 0;
   const int stage_bytes = kAStageBytes + (bn / 2) * 128;
   int stages = (227 * 1024 - 3072 - 8192 - epi_bytes) / stage_bytes;
@@ -607,9 +604,8 @@ int vcg_conv_fwd_tc2(const vcg_conv_desc* d, const void* x, const void* w, const
   if (grid > 2 * a.num_pair_tiles) grid = 2 * a.num_pair_tiles;
   if (!a.ring) {
     // wave quantisation: run the whole rounds as BN = 256 tiles and cut the left-over tiles into two BN = 128 halves
-    static const bool no_tail = getenv("VCG_NO_TAIL") && getenv("VCG_NO_TAIL")[0] == '1';      // A/B timing switch
     const int npairs = grid / 2, full = a.num_pair_tiles / npairs, rem = a.num_pair_tiles % npairs;
-    if (!no_tail && bn == 256 && full >= 1 && rem > 0 && 2 * rem <= npairs) { a.tail_r = rem; a.full_per_pair = full; }
+    if (bn == 256 && full >= 1 && rem > 0 && 2 * rem <= npairs) { a.tail_r = rem; a.full_per_pair = full; }
   }
   conv_tc2_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmTB, tmLR, a);
   VCG_CHECK_LAUNCH("conv_tc2_kernel");

@@ -264,7 +264,6 @@ bool fold_geometry(const vcg_conv_desc* d, FoldGeom* g) {
   if (fixed + 3 * kAStage > 227 * 1024) return false;
   int stages = static_cast<int>((227 * 1024 - fixed) / kAStage);
   if (stages > 8) stages = 8;
-  { const char* e = getenv("VCG_FOLD_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }   // tuning experiment
   g->stages = stages;
   g->smem = fixed + static_cast<size_t>(stages) * kAStage;
   return true;

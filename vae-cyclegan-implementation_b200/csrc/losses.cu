@@ -50,8 +50,16 @@ __global__ void __launch_bounds__(256)
 mse_const_kernel(const float* __restrict__ d, long long n, float target, float scale, float* __restrict__ out,
                  float* __restrict__ gd) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(gd)) & 15) == 0;
+  const long long n4 = vec ? (n >> 2) : 0;
   float acc = 0.f;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 x = reinterpret_cast<const float4*>(d)[i];
+    const float e0 = x.x - target, e1 = x.y - target, e2 = x.z - target, e3 = x.w - target;
+    acc += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+    if (gd) reinterpret_cast<float4*>(gd)[i] = make_float4(2.f * scale * e0, 2.f * scale * e1, 2.f * scale * e2, 2.f * scale * e3);
+  }
+  for (long long i = (n4 << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float e = d[i] - target;
     acc += e * e;
     if (gd) gd[i] = scale * 2.f * e;
@@ -64,16 +72,27 @@ __global__ void __launch_bounds__(256)
 kl_kernel(const float* __restrict__ mu, const float* __restrict__ lv, long long n, float scale, float* __restrict__ out,
           float* __restrict__ gmu, float* __restrict__ glv) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(mu) | reinterpret_cast<uintptr_t>(lv) | reinterpret_cast<uintptr_t>(gmu) |
+                     reinterpret_cast<uintptr_t>(glv)) & 15) == 0;
+  const long long n4 = vec ? (n >> 2) : 0;
   float acc = 0.f;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float m = mu[i], l = lv[i];
+  auto one = [&](float m, float l, float& gm, float& gl) {
     const float lc = fminf(fmaxf(l, -10.f), 10.f);
     const float e = expf(lc);
     acc += 1.f + lc - m * m - e;
-    if (gmu) {
-      gmu[i] = scale * m;                                            // d(-0.5*mean(...))/dmu = mu/N
-      glv[i] = (l >= -10.f && l <= 10.f) ? -0.5f * scale * (1.f - e) : 0.f;
-    }
+    gm = scale * m;                                                  // d(-0.5*mean(...))/dmu = mu/N
+    gl = (l >= -10.f && l <= 10.f) ? -0.5f * scale * (1.f - e) : 0.f;
+  };
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 m = reinterpret_cast<const float4*>(mu)[i], l = reinterpret_cast<const float4*>(lv)[i];
+    float4 gm, gl;
+    one(m.x, l.x, gm.x, gl.x); one(m.y, l.y, gm.y, gl.y); one(m.z, l.z, gm.z, gl.z); one(m.w, l.w, gm.w, gl.w);
+    if (gmu) { reinterpret_cast<float4*>(gmu)[i] = gm; reinterpret_cast<float4*>(glv)[i] = gl; }
+  }
+  for (long long i = (n4 << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gm, gl;
+    one(mu[i], lv[i], gm, gl);
+    if (gmu) { gmu[i] = gm; glv[i] = gl; }
   }
   acc = block_sum(acc);
   if (threadIdx.x == 0) atomicAdd(out, acc);
@@ -194,14 +213,68 @@ dhead_bwd1_kernel(const T* __restrict__ x, const float* __restrict__ w, const fl
 
 __global__ void __launch_bounds__(256)
 dhead_bwd2_kernel(const float* __restrict__ w, const float* __restrict__ wnorm2, const float* __restrict__ scratch,
-                  const float* __restrict__ gs, int n, int k, float* __restrict__ dw, float* __restrict__ dbias) {
+                  const float* __restrict__ gs, int n, int k, float* __restrict__ dw, float* __restrict__ dbias, int dw_c) {
   const float n2 = *wnorm2, inv = rsqrtf(n2), coef = scratch[k] / n2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < k) dw[i] += (scratch[i] - coef * w[i]) * inv;
+  // dw_c > 0: dw is the OIHW gradient of the [1, dw_c, kh, kw] filter ((h,w,c) index i -> c * (k / dw_c) + pixel)
+  if (i < k) dw[dw_c > 0 ? (i % dw_c) * (k / dw_c) + i / dw_c : i] += (scratch[i] - coef * w[i]) * inv;
   if (i == 0 && dbias) {
     float s = 0.f;
     for (int r = 0; r < n; ++r) s += gs[r];
     dbias[0] += s;
+  }
+}
+
+// Spectral-norm power iteration of a 1 x k weight matrix (torch/nn/utils/spectral_norm.py:92-114 as run by every training
+// forward of Networks.py:248), the (h, w, c)-ordered copy of the filter that vcg_dhead_* read, and
+// aux = {sigma = u . (W v), |W|}.  With one output row the iteration converges in one step: v = W u / |W u|, u = +-1.
+// Two small launches: (a) one block per 32-channel tile transposes it through shared memory (both sides coalesced) and
+// accumulates sum w^2 (and sum w*v_stale for the eval-mode sigma); (b) writes v and finishes u / aux.
+//   scratch (3 doubles, zeroed by the caller): {sum w^2, sum w * v_old, u_old}
+__global__ void __launch_bounds__(256)
+dhead_prepare_a_kernel(const float* __restrict__ w, int c, int hw, const float* __restrict__ u, const float* __restrict__ v,
+                       float* __restrict__ w_hwc, double* __restrict__ scratch) {
+  extern __shared__ float tile[];                          // [32][hw + 1]
+  const int c0 = blockIdx.x * 32, t = threadIdx.x, pitch = hw + 1;
+  const int nch = min(32, c - c0);
+  double ww = 0.0, wv = 0.0;
+  for (int i = t; i < nch * hw; i += 256) {
+    const int ch = i / hw, px = i - ch * hw;
+    const float x = w[static_cast<size_t>(c0 + ch) * hw + px];
+    tile[ch * pitch + px] = x;
+    ww += static_cast<double>(x) * x;
+    wv += static_cast<double>(x) * v[static_cast<size_t>(c0 + ch) * hw + px];
+  }
+  __syncthreads();
+  if (w_hwc)
+    for (int i = t; i < nch * hw; i += 256) {
+      const int px = i / nch, ch = i - px * nch;
+      w_hwc[static_cast<size_t>(px) * c + c0 + ch] = tile[ch * pitch + px];
+    }
+  ww = warp_sum_d(ww);
+  wv = warp_sum_d(wv);
+  if ((t & 31) == 0) { atomicAdd(scratch, ww); atomicAdd(scratch + 1, wv); }
+  if (blockIdx.x == 0 && t == 0) scratch[2] = static_cast<double>(u[0]);
+}
+
+__global__ void __launch_bounds__(256)
+dhead_prepare_b_kernel(const float* __restrict__ w, int k, float* __restrict__ u, float* __restrict__ v,
+                       float* __restrict__ aux, const double* __restrict__ scratch, int do_iter) {
+  const double ww = scratch[0];
+  const float wnorm = static_cast<float>(sqrt(ww)), u0 = static_cast<float>(scratch[2]);
+  const float denom = fmaxf(fabsf(u0) * wnorm, 1e-12f);                     // |W^T u| = |u| |W|
+  if (do_iter)
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < k; i += gridDim.x * 256) v[i] = w[i] * u0 / denom;   // v = normalize(W^T u)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float un = u0, s;
+    if (do_iter) {
+      s = static_cast<float>(static_cast<double>(u0) * ww / denom);          // W v with the v written above
+      un = s / fmaxf(fabsf(s), 1e-12f);                                       // u = normalize(W v)
+      u[0] = un;
+    } else {
+      s = static_cast<float>(scratch[1]);                                     // W v_stale (eval mode)
+    }
+    if (aux) { aux[0] = un * s; aux[1] = wnorm; }
   }
 }
 
@@ -273,6 +346,21 @@ extern "C" int vcg_reparam_bwd(int32_t dtype, const float* mu, int32_t mu_pitch,
   return VCG_OK;
 }
 
+extern "C" int vcg_dhead_prepare(const float* w_oihw, int32_t c, int32_t hw, float* u, float* v, float* w_hwc, float* aux,
+                                 double* scratch, int32_t do_iter, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VCG_REQUIRE(w_oihw && u && v && scratch && c > 0 && hw > 0, VCG_E_INVALID, "dhead_prepare: null / empty argument");
+  VCG_REQUIRE(static_cast<size_t>(32) * (hw + 1) * sizeof(float) <= 48 * 1024, VCG_E_UNSUPPORTED, "dhead_prepare: %d taps", hw);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, 3 * sizeof(double), stream);
+  VCG_REQUIRE(e == cudaSuccess, VCG_E_CUDA, "dhead_prepare: memset: %s", cudaGetErrorString(e));
+  dhead_prepare_a_kernel<<<(c + 31) / 32, 256, static_cast<size_t>(32) * (hw + 1) * sizeof(float), stream>>>(w_oihw, c, hw, u, v, w_hwc, scratch);
+  VCG_CHECK_LAUNCH("dhead_prepare_a_kernel");
+  const int k = c * hw;
+  dhead_prepare_b_kernel<<<do_iter ? (k + 2047) / 2048 : 1, 256, 0, stream>>>(w_oihw, k, u, v, aux, scratch, do_iter);
+  VCG_CHECK_LAUNCH("dhead_prepare_b_kernel");
+  return VCG_OK;
+}
+
 extern "C" int vcg_dhead_fwd(int32_t dtype, const void* x, const float* w_khwc, const float* bias, int32_t n, int32_t k,
                              float* score, float* wnorm2, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -293,7 +381,8 @@ extern "C" int vcg_dhead_fwd(int32_t dtype, const void* x, const float* w_khwc, 
 }
 
 extern "C" int vcg_dhead_bwd(int32_t dtype, const void* x, const float* w_khwc, const float* wnorm2, const float* gscore,
-                             int32_t n, int32_t k, void* dx, float* dw, float* dbias, float* scratch, void* stream_) {
+                             int32_t n, int32_t k, void* dx, float* dw, float* dbias, float* scratch, int32_t dw_c,
+                             void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VCG_REQUIRE(k % 8 == 0, VCG_E_UNSUPPORTED, "dhead: k=%d must be a multiple of 8", k);
   cudaError_t e = cudaMemsetAsync(scratch + k, 0, sizeof(float), stream);
@@ -308,7 +397,8 @@ extern "C" int vcg_dhead_bwd(int32_t dtype, const void* x, const float* w_khwc, 
                                                                  n, k, static_cast<__nv_bfloat16*>(dx), scratch);
   VCG_CHECK_LAUNCH("dhead_bwd1_kernel");
   if (dw) {
-    dhead_bwd2_kernel<<<(k + 255) / 256, 256, 0, stream>>>(w_khwc, wnorm2, scratch, gscore, n, k, dw, dbias);
+    VCG_REQUIRE(dw_c >= 0 && (dw_c == 0 || k % dw_c == 0), VCG_E_INVALID, "dhead_bwd: dw_c=%d does not divide k=%d", dw_c, k);
+    dhead_bwd2_kernel<<<(k + 255) / 256, 256, 0, stream>>>(w_khwc, wnorm2, scratch, gscore, n, k, dw, dbias, dw_c);
     VCG_CHECK_LAUNCH("dhead_bwd2_kernel");
   }
   return VCG_OK;

@@ -203,8 +203,6 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant
 }  // namespace
 
 bool vcg_wgrad2_supported(const vcg_conv_desc* d, int dy_c) {
-  static const bool off = getenv("VCG_WTC2") && getenv("VCG_WTC2")[0] == '0';        // A/B timing switch
-  if (off) return false;
   if (d->c % 64 != 0 || d->kwc_pad != d->kw * d->c) return false;
   if (d->cout % 256 != 0 || dy_c != d->cout) return false;
   if ((d->kwc_pad / 64) % 4 != 0) return false;

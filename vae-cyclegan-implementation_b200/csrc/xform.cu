@@ -224,9 +224,12 @@ xform_fwd_kernel(const T* __restrict__ src, const float* __restrict__ mr, const 
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (v[j] - sf[j]) * sc[j];
       }
-      if (p.act) {
+      if (p.act == VCG_ACT_RELU || p.act == VCG_ACT_LEAKY) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], p.act);
+      } else if (p.act) {          // Tanh / Sigmoid (CaSb's other choices): cold path
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) v[j] = act_apply_any(v[j], p.act);
       }
       if (rbase) {
         float r[8];
@@ -284,9 +287,12 @@ xform_fwd_shuffle_kernel(const T* __restrict__ src, const float* __restrict__ mr
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (v[j] - sf[j]) * sc[j];
       }
-      if (p.act) {
+      if (p.act == VCG_ACT_RELU || p.act == VCG_ACT_LEAKY) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], p.act);
+      } else if (p.act) {          // Tanh / Sigmoid (CaSb's other choices): cold path
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) v[j] = act_apply_any(v[j], p.act);
       }
       if (rbase) {
         float r[8];
@@ -967,8 +973,6 @@ static int pix_chunk(int hw, int n, int zc) {
 // several waves for load balance.  mult = blocks per SM aimed for (measured on B200, tools/bench_xform.py:
 // InstanceNorm backward 1024ch 16x16: 55 us at 8, 37 us at 2; 64ch 256x256: 291 us at 8, 376 us at 2).
 static int pix_chunk_fast(int hw, int n, int zc, int cg_total, int mult) {
-  static const int force = getenv("VCG_XF_WAVES") ? atoi(getenv("VCG_XF_WAVES")) : 0;      // A/B timing switch
-  if (force > 0) mult = force;
   const int cgl = cg_total < 32 ? cg_total : 32;
   const int step = kXbUmax * (256 / cgl);                  // pixels one block covers per unrolled iteration
   long long want = static_cast<long long>(mult) * vcg_num_sms();

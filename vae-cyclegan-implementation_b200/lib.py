@@ -15,6 +15,7 @@ ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 MODE_PLAIN, MODE_SHUFFLE, MODE_UNSHUFFLE, MODE_PAD_S2D = 0, 1, 2, 3
 WMAP_PLAIN, WMAP_UNSHUFFLE, WMAP_S2D = 0, 1, 2
 ADAM_TICK, ADAM_GRAD_BF16, ADAM_ZERO_GRAD = 1, 2, 4
+WGRAD_ALLOW_SIMT = 4
 
 i32 = C.c_int32
 
@@ -97,7 +98,9 @@ _SIGS = {
                                  C.c_void_p]),
     "vcg_dhead_fwd": (C.c_int, [i32, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vcg_dhead_bwd": (C.c_int, [i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, C.c_void_p,
-                                C.c_void_p, C.c_void_p, C.c_void_p]),
+                                C.c_void_p, C.c_void_p, i32, C.c_void_p]),
+    "vcg_dhead_prepare": (C.c_int, [C.c_void_p, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i32,
+                                    C.c_void_p]),
     "vcg_adam_multi": (C.c_int, [C.c_void_p, i32, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                  i32, C.c_void_p]),
     "vcg_cast_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, i32, C.c_void_p]),

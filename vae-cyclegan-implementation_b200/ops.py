@@ -256,14 +256,15 @@ def conv_dgrad(spec: ConvSpec, dy_pad, w_dgrad, dxp):
     return dxp
 
 
-def conv_wgrad(spec: ConvSpec, x_pad, dy_pad, dw_packed):
-    """dw_packed[cout_pad,kh,kwc_pad] += wgrad(x_pad, dy) ; dy_pad carries a zero halo of (k-1)."""
+def conv_wgrad(spec: ConvSpec, x_pad, dy_pad, dw_packed, allow_simt=False):
+    """dw_packed[cout_pad,kh,kwc_pad] += wgrad(x_pad, dy) ; dy_pad carries a zero halo of (k-1).
+    allow_simt: shapes no tensor-core kernel takes may run on the (slow) SIMT kernel instead of raising."""
     n, hp, wp, c = x_pad.shape
     halo_h, halo_w = spec.pkh - 1, spec.pkw - 1
     assert halo_h == halo_w
     d = L.ConvDesc(dtype=L.dtype_code(x_pad.dtype), n=n, hp=hp, wp=wp, c=c, kh=spec.pkh, kw=spec.pkw,
                    kwc_pad=spec.kwc_pad, cout=spec.co, cout_pad=spec.cout_pad, out_c=dy_pad.shape[-1], act=0, stats=0,
-                   flat=0, out_f32=0)
+                   flat=L.WGRAD_ALLOW_SIMT if allow_simt else 0, out_f32=0)
     assert dy_pad.shape[1] == hp - spec.pkh + 1 + 2 * halo_h
     tok = _rec("conv_wgrad", spec.flops(n, hp - spec.pkh + 1, wp - spec.pkw + 1), f"{spec.ci}->{spec.co} k{spec.kh} @{hp - spec.pkh + 1}")
     L.check(L.load().vcg_conv_wgrad(C.byref(d), L.ptr(x_pad), L.ptr(dy_pad), halo_h, dy_pad.shape[-1], L.ptr(dw_packed),
@@ -446,11 +447,27 @@ def dhead_fwd(x, w_khwc, bias, score, wnorm2):
 
 
 @_profiled("dhead_bwd")
-def dhead_bwd(x, w_khwc, wnorm2, gscore, dx, dw, dbias, scratch):
+def dhead_bwd(x, w_khwc, wnorm2, gscore, dx, dw, dbias, scratch, dw_c=0):
+    """dw_c = 0: dw is a (h, w, c)-ordered vector; dw_c = C: dw is the OIHW gradient tensor of the [1, C, kh, kw] filter
+    (accumulated in place, e.g. a view of the optimiser's flat gradient buffer)."""
     n = x.shape[0]
     k = x[0].numel()
+    if dw is not None:
+        assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == k
     L.check(L.load().vcg_dhead_bwd(L.dtype_code(x.dtype), L.ptr(x), L.ptr(w_khwc), L.ptr(wnorm2), L.ptr(gscore), n, k,
-                                   L.ptr(dx), L.ptr(dw), L.ptr(dbias), L.ptr(scratch), L.stream_ptr()), "vcg_dhead_bwd")
+                                   L.ptr(dx), L.ptr(dw), L.ptr(dbias), L.ptr(scratch), dw_c, L.stream_ptr()), "vcg_dhead_bwd")
+
+
+@_profiled("dhead_prepare")
+def dhead_prepare(w_oihw, u, v, w_hwc, aux, do_iter, scratch=None):
+    """spectral-norm power iteration (in place on u, v when do_iter), (h, w, c) filter copy, aux = {sigma, |W|};
+    scratch: 3 doubles of caller-owned device memory (allocated here when omitted)"""
+    co, c, kh, kw = w_oihw.shape
+    assert co == 1 and w_oihw.dtype == torch.float32 and w_oihw.is_contiguous()
+    if scratch is None:
+        scratch = torch.empty(3, dtype=torch.float64, device=w_oihw.device)
+    L.check(L.load().vcg_dhead_prepare(L.ptr(w_oihw), c, kh * kw, L.ptr(u), L.ptr(v), L.ptr(w_hwc), L.ptr(aux),
+                                       L.ptr(scratch), 1 if do_iter else 0, L.stream_ptr()), "vcg_dhead_prepare")
 
 
 @_profiled("adam_multi")

@@ -17,7 +17,14 @@ import torch
 from . import lib as L
 from . import ops
 
-_STATE = {"dtype": torch.bfloat16, "input_grads": True}
+_STATE = {"dtype": torch.bfloat16, "input_grads": True, "unfolded_max_hw": 0}
+
+
+def set_unfolded_max_hw(hw):
+    """Reflect-halo adjoint of padded-input gradients: activations of more than `hw` pixels get the in-place
+    fold_halo launch (their gather then takes the fast single-position path); smaller planes skip the launch and let
+    the gather read the mirrors itself (one launch less where launches, not bytes, set the time).  0: always fold."""
+    _STATE["unfolded_max_hw"] = int(hw)
 
 
 def set_precision(mode):
@@ -495,7 +502,7 @@ class Plan:
             s = [(t, L.MODE_PLAIN, 0) for t in dense.get(act.id, ())]
             for c in act.consumers:
                 if isinstance(c, ConvNode) and c in dxp:
-                    s.append((dxp[c], c.mode, c.pad, True))      # halo already folded (see conv_dgrad below)
+                    s.append((dxp[c][0], c.mode, c.pad, dxp[c][1]))      # halo folded already? (see conv_dgrad below)
             for p in act.passthrough:
                 s.extend(sources(p))
             return s
@@ -516,20 +523,16 @@ class Plan:
                 scratch = torch.empty(k + 8, dtype=torch.float32, device=dev)
                 h = node.holder
                 want_w = _wants_grad(h.weight_orig)
-                dwk = ops.zero_(torch.empty(k, dtype=torch.float32, device=dev)) if want_w else None
-                db = ops.zero_(torch.empty(4, dtype=torch.float32, device=dev)) if want_w else None
-                ops.dhead_bwd(x, wk, wn2, gs, dx, dwk, db, scratch)
+                gw = gb = None
                 if want_w:
-                    co, ci, kh, kw = h.weight_orig.shape
-                    gw = dwk.view(kh, kw, ci).permute(2, 0, 1).reshape(co, ci, kh, kw)
+                    # the head's gradient is written straight into .grad in OIHW order (no temporaries, no torch ops)
                     if h.weight_orig.grad is None:
-                        h.weight_orig.grad = gw.contiguous()
-                    else:
-                        h.weight_orig.grad.add_(gw)
+                        h.weight_orig.grad = torch.zeros_like(h.weight_orig, memory_format=torch.contiguous_format)
                     if h.bias.grad is None:
-                        h.bias.grad = db[:1].clone()
-                    else:
-                        h.bias.grad.add_(db[:1])
+                        h.bias.grad = torch.zeros_like(h.bias)
+                    gw, gb = h.weight_orig.grad, h.bias.grad
+                ops.dhead_bwd(x, wk, wn2, gs, dx, gw, gb, scratch, dw_c=h.weight_orig.shape[1] if want_w else 0)
+                if want_w:
                     _mark_grad_written(h.weight_orig)
                     for t in _TRACKERS:
                         t.contributed(h)
@@ -583,7 +586,9 @@ class Plan:
                                          clear_halo=True)
                 xp = run.xp_of_node[node]
                 if want_w:
-                    ops.conv_wgrad(spec, xp, dy, dw)       # accumulates; added to .grad by flush_grads()
+                    # accumulates; added to .grad by flush_grads().  Maps below 8x8 (inputs smaller than the 256x256 the
+                    # networks are built for) have no tensor-core weight-gradient kernel: SIMT kernel, on request
+                    ops.conv_wgrad(spec, xp, dy, dw, allow_simt=a0.h * a0.w < 64)
                     pc.mark_pending(want_b)
                 if needs_dx(node.inp):
                     pc.refresh(dtype)
@@ -591,8 +596,10 @@ class Plan:
                     ops.conv_dgrad(spec, dy, pc.wkT, g)
                     # adjoint of the reflect padding: fold the halo into the interior once, here, so that every
                     # gather of this gradient (it can feed two activations through a residual) reads one position
-                    ops.fold_halo_(g, node.mode, node.pad, node.inp.h, node.inp.w, node.inp.c)
-                    dxp[node] = g
+                    folded = node.inp.h * node.inp.w > _STATE["unfolded_max_hw"]
+                    if folded:
+                        ops.fold_halo_(g, node.mode, node.pad, node.inp.h, node.inp.w, node.inp.c)
+                    dxp[node] = (g, folded)
                 if want_w:
                     # FusedAdam.track: when this was the bucket's last contribution, its tail (unpack, all-reduce, Adam,
                     # RE-PACK of the filters) starts on the side stream behind the event recorded here -- i.e. behind
@@ -614,12 +621,33 @@ class Plan:
         return res
 
 
-def head_weight(holder):
-    """(1,512,16,16) weight_orig -> fp32 vector in (h,w,c) order, cached by version."""
+def head_state(holder, iterate=False):
+    """Derived state of the spectral-normalised head (Networks.py:248): the (h, w, c)-ordered fp32 filter vector the
+    head kernels read and aux = {sigma, |W|}, in PERSISTENT buffers (stable addresses: CUDA-graph safe), refreshed by
+    one vcg_dhead_prepare launch when weight_orig changed; iterate=True also runs the reference's power iteration
+    (in place on weight_u / weight_v) unless it already ran on these very W, u, v -- with a 1 x K matrix the
+    iteration is idempotent (u = +-1 exactly), so the reference's repeated iterations within a step are skipped."""
     w = holder.weight_orig
-    key = (w._version, getattr(w, "_vcg_epoch", 0), w.data_ptr(), w.device)
+    base = (w._version, getattr(w, "_vcg_epoch", 0), w.data_ptr(), w.device)
     cache = holder.__dict__.setdefault("_vcg_head", {})
-    if cache.get("key") != key:
-        cache["w"] = w.detach()[0].permute(1, 2, 0).contiguous().view(-1)
-        cache["key"] = key
-    return cache["w"]
+    need_copy = cache.get("key") != base
+    it_key = (base, holder.weight_u._version, holder.weight_v._version, holder.weight_u.data_ptr())
+    need_iter = iterate and cache.get("iter_key") != it_key
+    if need_copy or need_iter:
+        if cache.get("w") is None or cache["w"].device != w.device:
+            cache["w"] = torch.empty(w[0].numel(), dtype=torch.float32, device=w.device)
+            cache["aux"] = torch.empty(2, dtype=torch.float32, device=w.device)
+            cache["scratch"] = torch.empty(3, dtype=torch.float64, device=w.device)
+        wd = w.detach()
+        if wd.dtype != torch.float32 or not wd.is_contiguous():
+            raise RuntimeError("spectral head: weight_orig must be contiguous fp32")
+        ops.dhead_prepare(wd, holder.weight_u, holder.weight_v, cache["w"], cache["aux"], need_iter, cache["scratch"])
+        cache["key"] = base
+        if need_iter:
+            cache["iter_key"] = it_key
+    return cache
+
+
+def head_weight(holder):
+    """(1,512,16,16) weight_orig -> fp32 vector in (h,w,c) order"""
+    return head_state(holder)["w"]
