@@ -51,17 +51,14 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=2, help="bounded CPU sample: batch of the reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=-1,
-                    help="independent passes of the step on two streams (vcg_b200.lanes): 1 on, 0 off, -1 auto "
-                         "(on when the per-GPU batch is small enough for sub-wave layers: <= 16)")
+    ap.add_argument("--lanes", type=int, default=1,
+                    help="independent passes of the step on two streams (vcg_b200.lanes): 1 on (library default), 0 off")
     ap.add_argument("--gpu-reference", type=int, default=-1,
                     help="time the unmodified reference through stock PyTorch on this GPU (informational): 1 on, 0 off, "
                          "-1 auto (on for the single-GPU run)")
     ap.add_argument("--overlap", type=int, default=-1,
                     help="gradient-bucket tails (unpack, all-reduce, Adam, re-pack) on the optimisers' side streams behind the "
                          "backward pass: 1 on, 0 off (same launches on the calling stream at step()), -1 library default")
-    ap.add_argument("--unfolded-max-hw", type=int, default=-1,
-                    help="plan.set_unfolded_max_hw: planes up to this many pixels skip the fold_halo launch (-1: library default)")
     ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32"], help="gradient all-reduce element type")
     ap.add_argument("--profile", type=int, default=1, help="1: external CUDA events around every launch inside the captured graph")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (vcg_b200.graph.GraphedStep)")
@@ -235,15 +232,13 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     lib.load()
     plan.set_precision(args.precision)
-    if args.unfolded_max_hw >= 0:
-        plan.set_unfolded_max_hw(args.unfolded_max_hw)
     from vcg_b200 import lanes
     if args.global_batch % world:
         raise SystemExit("global batch must be divisible by the number of GPUs")
     per = args.global_batch // world
-    # two lanes pay when layers cannot fill the machine (16x16 maps at a small per-GPU batch); at batch >= 32 every
-    # GEMM is several waves long and the serial schedule measured the same (80.24 vs 80.37 ms at batch 64)
-    use_lanes = bool(args.lanes) if args.lanes >= 0 else per <= 16
+    # two lanes pay most when layers cannot fill the machine (16x16 maps at a small per-GPU batch: 15.7 -> 13.2 ms at
+    # batch 8) and never cost: 81.0 -> 80.3 ms at batch 64, 43.3 -> 42.0 at batch 32 (CUDA-graph replay, one B200)
+    use_lanes = bool(args.lanes)
     lanes.set_enabled(use_lanes)
 
     torch.manual_seed(1234)

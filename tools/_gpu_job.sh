@@ -1,9 +1,8 @@
-# round-2 GPU job 7: suite, step at batch 64 / 8 after the epilogue-register and dhead_prepare fixes, unfolded-halo A/B
-python -m pytest tests -m gpu -q > gpurun_out/r2_t7.log 2>&1; echo "suite rc=$?"
-grep -E "^FAILED|^ERROR|passed|failed" gpurun_out/r2_t7.log | cut -c1-200 | tail -12
-grep -E "^E  " gpurun_out/r2_t7.log | cut -c1-250 | head -12
-grep -E "\[config|\[white" gpurun_out/r2_t7.log | cut -c1-300
-B="--steps 10 --warmup 3 --no-cpu-baseline --gpu-reference 0 --profile 0"
-for gb in 64 8; do for uf in 0 1024 4096; do python bench.py --global-batch $gb --unfolded-max-hw $uf $B > gpurun_out/r2_b7_gb${gb}_uf${uf}.log 2>&1; echo "gb$gb unfolded$uf $(tail -1 gpurun_out/r2_b7_gb${gb}_uf${uf}.log | cut -c90-200)"; done; done
-python bench.py --global-batch 16 $B > gpurun_out/r2_b7_gb16.log 2>&1; echo "gb16 $(tail -1 gpurun_out/r2_b7_gb16.log | cut -c90-200)"
-python bench.py --global-batch 32 $B > gpurun_out/r2_b7_gb32.log 2>&1; echo "gb32 $(tail -1 gpurun_out/r2_b7_gb32.log | cut -c90-200)"
+# round-2 GPU job 9 (8 GPUs): the headline scaling points
+T="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+B="--steps 10 --warmup 3 --profile 0"
+$T --nproc-per-node 8 --master-port 29511 bench.py --gpus 8 $B > gpurun_out/r2_b9_n8.log 2>&1; echo "n8 $(grep '^{' gpurun_out/r2_b9_n8.log | cut -c90-200)"
+$T --nproc-per-node 4 --master-port 29512 bench.py --gpus 4 $B > gpurun_out/r2_b9_n4.log 2>&1; echo "n4 $(grep '^{' gpurun_out/r2_b9_n4.log | cut -c90-200)"
+$T --nproc-per-node 8 --master-port 29513 bench.py --gpus 8 $B --overlap 0 > gpurun_out/r2_b9_n8_ov0.log 2>&1; echo "n8 overlap0 $(grep '^{' gpurun_out/r2_b9_n8_ov0.log | cut -c90-200)"
+$T --nproc-per-node 8 --master-port 29514 bench.py --gpus 8 $B --wire fp32 > gpurun_out/r2_b9_n8_fp32.log 2>&1; echo "n8 wire fp32 $(grep '^{' gpurun_out/r2_b9_n8_fp32.log | cut -c90-200)"
+tail -2 gpurun_out/r2_b9_n8.log | cut -c1-300

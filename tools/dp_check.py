@@ -82,7 +82,10 @@ def main():
         out = {"world": world, "metrics_worst_rel": worst, "grad_rel_l2": gerr, "weights_worst_rel_l2": werr,
                "weights_worst_key": wkey, "bias_buffer_max_abs_diff": berr,
                "G_loss_dp": m_dp["G_loss"], "G_loss_single": m_1["G_loss"],
-               "ok": bool(worst < 1e-4 and gerr < 1e-3 and werr < 1e-3 and berr <= 4.1e-4)}
+               "wire": os.environ.get("DP_WIRE", "fp32"), "steps": steps,
+               # bf16 on the wire rounds every rank's gradient to 8 bits of mantissa before the sum: 2^-9 relative per element
+               "ok": bool(worst < 1e-4 and gerr < (1e-3 if os.environ.get("DP_WIRE", "fp32") == "fp32" else 6e-3) and
+                          werr < (1e-3 if os.environ.get("DP_WIRE", "fp32") == "fp32" else 2e-2) and berr <= 4.1e-4)}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -17,14 +17,7 @@ import torch
 from . import lib as L
 from . import ops
 
-_STATE = {"dtype": torch.bfloat16, "input_grads": True, "unfolded_max_hw": 0}
-
-
-def set_unfolded_max_hw(hw):
-    """Reflect-halo adjoint of padded-input gradients: activations of more than `hw` pixels get the in-place
-    fold_halo launch (their gather then takes the fast single-position path); smaller planes skip the launch and let
-    the gather read the mirrors itself (one launch less where launches, not bytes, set the time).  0: always fold."""
-    _STATE["unfolded_max_hw"] = int(hw)
+_STATE = {"dtype": torch.bfloat16, "input_grads": True}
 
 
 def set_precision(mode):
@@ -502,7 +495,7 @@ class Plan:
             s = [(t, L.MODE_PLAIN, 0) for t in dense.get(act.id, ())]
             for c in act.consumers:
                 if isinstance(c, ConvNode) and c in dxp:
-                    s.append((dxp[c][0], c.mode, c.pad, dxp[c][1]))      # halo folded already? (see conv_dgrad below)
+                    s.append((dxp[c], c.mode, c.pad, True))      # halo already folded (see conv_dgrad below)
             for p in act.passthrough:
                 s.extend(sources(p))
             return s
@@ -596,10 +589,10 @@ class Plan:
                     ops.conv_dgrad(spec, dy, pc.wkT, g)
                     # adjoint of the reflect padding: fold the halo into the interior once, here, so that every
                     # gather of this gradient (it can feed two activations through a residual) reads one position
-                    folded = node.inp.h * node.inp.w > _STATE["unfolded_max_hw"]
-                    if folded:
-                        ops.fold_halo_(g, node.mode, node.pad, node.inp.h, node.inp.w, node.inp.c)
-                    dxp[node] = (g, folded)
+                    # (skipping this launch for small planes and letting the gather read the mirrors itself measured
+                    #  SLOWER: batch 8 13.19 -> 13.69 ms, batch 64 81.0 -> 84.1 ms; the single-position gather is the fast one)
+                    ops.fold_halo_(g, node.mode, node.pad, node.inp.h, node.inp.w, node.inp.c)
+                    dxp[node] = g
                 if want_w:
                     # FusedAdam.track: when this was the bucket's last contribution, its tail (unpack, all-reduce, Adam,
                     # RE-PACK of the filters) starts on the side stream behind the event recorded here -- i.e. behind
