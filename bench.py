@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--overlap", type=int, default=-1,
                     help="gradient-bucket tails (unpack, all-reduce, Adam, re-pack) on the optimisers' side streams behind the "
                          "backward pass: 1 on, 0 off (same launches on the calling stream at step()), -1 library default")
+    ap.add_argument("--side-streams", type=int, default=0, help="FusedAdam.side_streams (0: library default)")
     ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32"], help="gradient all-reduce element type")
     ap.add_argument("--profile", type=int, default=1, help="1: external CUDA events around every launch inside the captured graph")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (vcg_b200.graph.GraphedStep)")
@@ -246,9 +247,11 @@ def run_ours(args):
     model.configure_optimizers(lr=2e-4)
     model.configure_loss(lambda_kl=1e-5, lambda_gan=1.0, lambda_identity=5.0, lambda_cycle=10.0, lambda_recon=1.0)
     model.train()
-    if args.overlap >= 0:
-        for o in (model.optimizer_G, model.optimizer_D):
+    for o in (model.optimizer_G, model.optimizer_D):
+        if args.overlap >= 0:
             o.overlap = bool(args.overlap)
+        if args.side_streams > 0:
+            o.side_streams = args.side_streams
     sync = None
     if world > 1:
         vdist.broadcast_state(model)

@@ -55,6 +55,11 @@ class PlanFunction(torch.autograd.Function):
 def run_plan(plan, inputs, eps_list=()):
     for x in inputs:
         require_cuda(x, "network input")
+        if x.device.index != torch.cuda.current_device():
+            # every kernel is enqueued on the CURRENT device's current stream (lib.stream_ptr): tensors of another GPU
+            # would be dereferenced in the wrong context
+            raise RuntimeError(f"network input lives on {x.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                               "call torch.cuda.set_device() (one process per GPU) first")
     keep = torch.is_grad_enabled()
     return PlanFunction.apply(plan, keep, tuple(eps_list), _anchor(inputs[0].device), *inputs)
 

@@ -102,9 +102,13 @@ class FusedAdam(torch.optim.Adam):
         self.keep_grads = False     # True: .grad survives step() (tests / tools that read gradients after a step)
         self.grad_scale = 1.0       # data-parallel averaging folded into the update (dist.py sets 1/world)
         self.sync = None            # dist.GradSync when data-parallel
-        self.overlap = True         # run the bucket tails on a side stream (joined by finish())
-        self._side = None
-        self._side_used = False
+        self.overlap = True         # run the bucket tails on side streams (joined by finish())
+        self.side_streams = 3       # buckets go round-robin over this many streams: the all-reduce of one bucket (NVLink)
+                                    # overlaps the unpack / Adam / re-pack of its neighbours (HBM)
+        self._sides = []
+        self._sides_used = set()
+        self._next_side = 0
+        self._tick_event = None
 
     # ---- buckets ----------------------------------------------------------------------------
     def set_owners(self, owners, bucket_params=BUCKET_PARAMS):
@@ -161,7 +165,9 @@ class FusedAdam(torch.optim.Adam):
                 b.hi = off
                 b.tables = {}
             self._flat = torch.zeros(off, dtype=torch.float32, device=dev)
-            self._m = self._v = self._wire = None
+            # moments: allocated (and zero-filled) HERE, on the calling stream, before any bucket tail can run on a side
+            # stream -- the tails of different buckets run on different streams and must not race with a lazy fill
+            self._m, self._v, self._wire = torch.zeros_like(self._flat), torch.zeros_like(self._flat), None
             self._zeroed = True
             for p in ps:
                 o = self._offsets[id(p)]
@@ -172,7 +178,9 @@ class FusedAdam(torch.optim.Adam):
     def wire_buffer(self):
         """bf16 image of the flat gradient buffer: what travels over NVLink (dist.GradSync)."""
         if self._wire is None or self._wire.device != self._flat.device:
-            self._wire = torch.zeros(self._flat.numel(), dtype=torch.bfloat16, device=self._flat.device)
+            # (uninitialised on purpose: every slice is written by the cast of its bucket before anything reads it, and a
+            #  fill launched from one bucket's stream would race with the casts of the others)
+            self._wire = torch.empty(self._flat.numel(), dtype=torch.bfloat16, device=self._flat.device)
         return self._wire
 
     def reduced_grad(self):
@@ -217,16 +225,15 @@ class FusedAdam(torch.optim.Adam):
 
     # ---- the update -----------------------------------------------------------------------------
     def _stream(self, dev):
-        if self._side is None or self._side.device != dev:
-            self._side = torch.cuda.Stream(device=dev)
-        return self._side
+        if not self._sides or self._sides[0].device != dev:
+            self._sides = [torch.cuda.Stream(device=dev) for _ in range(max(1, self.side_streams))]
+        s = self._sides[self._next_side % len(self._sides)]
+        self._next_side += 1
+        return s
 
     def _state_for(self, p):
         st = self.state[p]
         if len(st) == 0:
-            if self._m is None or self._m.device != self._flat.device:
-                self._m = torch.zeros_like(self._flat)
-                self._v = torch.zeros_like(self._flat)
             st["step"] = torch.tensor(0.0, dtype=torch.float32)
             o = self._offsets.get(id(p))
             if o is not None and p.is_contiguous():
@@ -275,6 +282,9 @@ class FusedAdam(torch.optim.Adam):
         dev = b.params[0].device
         if not b.params[0].is_cuda:
             raise RuntimeError("FusedAdam: CUDA parameters required (no CPU fallback)")
+        if dev.index != torch.cuda.current_device():
+            raise RuntimeError(f"FusedAdam: parameters live on {dev} but the current CUDA device is "
+                               f"cuda:{torch.cuda.current_device()} (kernels are enqueued on the current device's streams)")
         self.flat_grad()
         cur = torch.cuda.current_stream(dev)
         side = self._stream(dev) if self.overlap else None
@@ -284,7 +294,7 @@ class FusedAdam(torch.optim.Adam):
                     side.wait_event(ev)
             else:
                 side.wait_stream(cur)
-            self._side_used = True
+            self._sides_used.add(side)
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
             if b.holders:
                 plan.flush_grads(b.holders)
@@ -300,15 +310,21 @@ class FusedAdam(torch.optim.Adam):
             beta1, beta2 = group["betas"]
             table, nchunks = self._table(b, wire)
             flags = 0
-            if not self._ticked:
+            ticking = not self._ticked
+            if ticking:
                 self._sync_step_counter(dev)
                 flags |= L.ADAM_TICK
                 self._ticked = True
+            elif side is not None and self._tick_event is not None:
+                side.wait_event(self._tick_event)       # the step counter / bias corrections advance once per step
             if wire == "bf16":
                 flags |= L.ADAM_GRAD_BF16
             elif not self.keep_grads:
                 flags |= L.ADAM_ZERO_GRAD
             ops.adam_multi(table, nchunks, self._dev_state, group["lr"], beta1, beta2, group["eps"], self.grad_scale, flags)
+            if ticking and side is not None:
+                self._tick_event = torch.cuda.Event()
+                self._tick_event.record(side)
             for p in b.params:        # the kernel wrote p behind autograd's back: invalidate packed copies
                 p._vcg_epoch = getattr(p, "_vcg_epoch", 0) + 1
             if b.holders:
@@ -352,6 +368,8 @@ class FusedAdam(torch.optim.Adam):
         self._dev_step += 1
         self._last = steps
         self._ticked = False
+        self._tick_event = None
+        self._next_side = 0
         for b in self._buckets:
             b.fired = False
         self._zeroed = not self.keep_grads      # consumed gradients were zeroed by the Adam / wire-cast kernels
@@ -360,9 +378,11 @@ class FusedAdam(torch.optim.Adam):
     @torch.no_grad()
     def finish(self):
         """Join the side stream: afterwards the calling stream sees the updated weights and their packed copies."""
-        if self._side_used:
-            self._side_used = False
-            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+        if self._sides_used:
+            cur = torch.cuda.current_stream(next(iter(self._sides_used)).device)
+            for s in self._sides_used:
+                cur.wait_stream(s)
+            self._sides_used = set()
 
     def state_dict(self):
         self.finish()
