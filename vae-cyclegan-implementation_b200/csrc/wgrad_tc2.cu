@@ -166,26 +166,40 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant
       }
     }
   } else if (warp >= 4) {
+    // Epilogue: dW += accumulator (red.global.add.v4.f32).  A thread owns one accumulator ROW (output channel), so a
+    // straight drain makes every red instruction hit 32 different filter rows (32 separate 16-byte atomics).  Each
+    // 32 x 32 block goes through a warp-private shared-memory tile instead, so that one instruction covers four rows
+    // x 128 contiguous bytes (4 cache lines instead of 32 sectors): at a per-GPU batch of 8 the reduction length is 32
+    // k-blocks and this epilogue, not the MMAs, paced the kernel.
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;
+    float* tile = reinterpret_cast<float*>(smem + S * kStage + 2048) + (warp - 4) * (32 * 36);
+    const int rr = lane >> 3, cc = (lane & 7) * 4;
     int as = 0; uint32_t aphase = 0;
     for (int item = pair; item < p.num_items; item += npairs) {
       int split, m_tile, khi, jc0;
       decode(item, split, m_tile, khi, jc0);
-      const int co = m_tile * 256 + rank * 128 + row;
+      const int co0 = m_tile * 256 + rank * 128 + quad * 32;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * 256);
-      float* dst = p.dw + static_cast<size_t>(co) * p.row_len + static_cast<size_t>(khi) * p.kwc_pad + jc0 * 64;
+      float* dst0 = p.dw + static_cast<size_t>(co0) * p.row_len + static_cast<size_t>(khi) * p.kwc_pad + jc0 * 64;
       for (int c0 = 0; c0 < 256; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
-        if (co < p.cout) {
+        __syncwarp();                                   // the previous block's reads of the tile are done
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            red_add_v4(dst + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                       __uint_as_float(r[j + 3]));
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(tile + lane * 36 + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + rr;
+          if (co0 + row < p.cout) {
+            const float4 v = *reinterpret_cast<const float4*>(tile + row * 36 + cc);
+            red_add_v4(dst0 + static_cast<size_t>(row) * p.row_len + c0 + cc, v.x, v.y, v.z, v.w);
+          }
         }
       }
       tc_fence_before();
@@ -237,12 +251,13 @@ int vcg_conv_wgrad_tc2(const vcg_conv_desc* d, const void* x, const void* dy, in
   a.cout = d->cout; a.row_len = d->kh * d->kwc_pad; a.kwc_pad = d->kwc_pad;
   a.idesc = umma_idesc_bf16(256, 256, 1, 1);
   a.dw = dw;
-  int stages = (227 * 1024 - 2048) / kStage;
+  constexpr int kEpiBytes = 4 * 32 * 36 * 4;            // warp-private transpose tiles of the epilogue
+  int stages = (227 * 1024 - 2048 - kEpiBytes) / kStage;
   if (stages > 6) stages = 6;
   if (stages > a.kb_per_split) stages = a.kb_per_split;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  const size_t smem = static_cast<size_t>(stages) * kStage + 2048;
+  const size_t smem = static_cast<size_t>(stages) * kStage + 2048 + kEpiBytes;
 
   CUtensorMap tmDy, tmX;
   const uint64_t es = 2;
