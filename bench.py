@@ -60,6 +60,7 @@ def parse():
                     help="gradient-bucket tails (unpack, all-reduce, Adam, re-pack) on the optimisers' side streams behind the "
                          "backward pass: 1 on, 0 off (same launches on the calling stream at step()), -1 library default")
     ap.add_argument("--side-streams", type=int, default=0, help="FusedAdam.side_streams (0: library default)")
+    ap.add_argument("--wgrad-side", type=int, default=-1, help="plan.set_wgrad_side (-1: library default)")
     ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32"], help="gradient all-reduce element type")
     ap.add_argument("--profile", type=int, default=1, help="1: external CUDA events around every launch inside the captured graph")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (vcg_b200.graph.GraphedStep)")
@@ -233,6 +234,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     lib.load()
     plan.set_precision(args.precision)
+    if args.wgrad_side >= 0:
+        plan.set_wgrad_side(bool(args.wgrad_side))
     from vcg_b200 import lanes
     if args.global_batch % world:
         raise SystemExit("global batch must be divisible by the number of GPUs")

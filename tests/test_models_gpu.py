@@ -410,6 +410,7 @@ def test_lanes_and_bucket_overlap_match_the_serial_step(env, arch):
 
     def run(concurrent):
         prev = lanes.set_enabled(concurrent)
+        plan.set_wgrad_side(concurrent)             # weight-gradient GEMMs on their chain's low-priority side stream
         try:
             torch.manual_seed(1234)
             m = getattr(N, CLS[arch])(**kw).cuda()
@@ -434,6 +435,7 @@ def test_lanes_and_bucket_overlap_match_the_serial_step(env, arch):
             return out, grads, {k: v.detach().clone() for k, v in m.state_dict().items()}
         finally:
             lanes.set_enabled(prev)
+            plan.set_wgrad_side(True)
 
     ms, gs, ws = run(False)
     mc, gc, wc = run(True)

@@ -58,8 +58,14 @@ class GraphedStep:
             o.capture_rollback()
         self._restore(snap)
         self.keys, self.vals = sink["keys"], sink["vals"]
+        # hyper-parameters are kernel ARGUMENTS baked into the captured launches
+        self._hyper = [self._hyper_of(o) for o in self.opts]
         self._stage_x = self._stage_y = self._copy_stream = self._staged_ready = self._stage_free = None
         self._staged_key = None
+
+    @staticmethod
+    def _hyper_of(opt):
+        return [(g["lr"], tuple(g["betas"]), g["eps"]) for g in opt.param_groups]
 
     def kernel_times(self):
         """[(family, flops or bytes, tag, milliseconds)] of the kernel launches of the LAST replay (profile=True)."""
@@ -113,6 +119,9 @@ class GraphedStep:
         host-to-device copy is issued on a side stream right after the graph launch, so it overlaps this step's
         compute instead of preceding the next one (what a pinned-memory data loader with non_blocking copies does).
         The caller must not modify the prefetched host tensors before the call that consumes them."""
+        if [self._hyper_of(o) for o in self.opts] != self._hyper:
+            raise RuntimeError("GraphedStep: an optimiser's lr / betas / eps changed after the capture; they are baked into "
+                               "the captured Adam launches -- build a new GraphedStep (e.g. once per lr-schedule step)")
         key = self._batch_key(batch)
         if self._staged_key is not None and key == self._staged_key:
             torch.cuda.current_stream().wait_event(self._staged_ready)

@@ -39,7 +39,7 @@ def _get(device):
         device = torch.device("cuda", torch.cuda.current_device())
     s = _LANES.get(device)
     if s is None:
-        s = _LANES[device] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+        s = _LANES[device] = (torch.cuda.Stream(device, priority=-1), torch.cuda.Stream(device, priority=-1))
     return s
 
 
@@ -58,6 +58,19 @@ def join_dirty(device=None):
             if s.device == cur.device:
                 cur.wait_stream(s)
                 _DIRTY.discard(s)
+
+
+_WGRAD = {}           # chain stream handle -> low-priority stream for that chain's weight-gradient GEMMs
+
+
+def wgrad_stream(chain):
+    """Side stream for the weight-gradient GEMMs of the backward pass running on `chain` (plan.run_backward): they are
+    off the critical path gather -> norm -> data gradient -> next layer, so they run at lower stream priority beside it."""
+    key = (chain.device, chain.cuda_stream)
+    s = _WGRAD.get(key)
+    if s is None:
+        s = _WGRAD[key] = torch.cuda.Stream(chain.device, priority=0)
+    return s
 
 
 class _Same:

@@ -62,7 +62,8 @@ class _Tracker:
     def tracks(self, holder):
         return id(holder) in self.count
 
-    def contributed(self, holder):
+    def contributed(self, holder, extra_stream=None):
+        """extra_stream: the side stream the weight-gradient GEMM was issued on, when it is not the current one"""
         c = self.count.get(id(holder))
         if c is None:
             return
@@ -70,10 +71,11 @@ class _Tracker:
         if b.fired:
             raise RuntimeError("FusedAdam.track: a weight gradient arrived after its bucket was handed to the optimiser "
                                "(more backward passes than announced)")
-        st = torch.cuda.current_stream()
-        ev = torch.cuda.Event()
-        ev.record(st)
-        b.events[st.cuda_stream] = ev
+        for st in (torch.cuda.current_stream(), extra_stream):
+            if st is not None:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                b.events[st.cuda_stream] = ev
         c[0] -= 1
         if c[0] == 0:
             b.remaining -= 1

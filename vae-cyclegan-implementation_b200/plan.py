@@ -17,7 +17,14 @@ import torch
 from . import lib as L
 from . import ops
 
-_STATE = {"dtype": torch.bfloat16, "input_grads": True}
+_STATE = {"dtype": torch.bfloat16, "input_grads": True, "wgrad_side": True}
+
+
+def set_wgrad_side(flag):
+    """True (default): the weight-gradient GEMMs of a backward pass run on a low-priority side stream of their chain
+    (they are off the critical path dY -> data gradient -> next layer's gather) and are joined when the pass ends.
+    Measured (CUDA-graph replay, one B200): batch 8 13.21 -> 12.76 ms, batch 16 22.49 -> 22.43, batch 64 80.93 -> 80.72."""
+    _STATE["wgrad_side"] = bool(flag)
 
 
 def set_precision(mode):
@@ -467,6 +474,7 @@ class Plan:
                 gs_off[nd] = gs_total
                 gs_total += n * nd.spec.co * 2
         gs_arena = None
+        wside, wkeep, cur_stream = None, [], None       # weight gradients on a side stream (set_wgrad_side)
         dense = {}        # act id -> list of dense NHWC grad tensors
         dxp = {}          # conv node -> padded-input gradient
         ext_mu, ext_lv, gscores = {}, {}, {}
@@ -581,7 +589,19 @@ class Plan:
                 if want_w:
                     # accumulates; added to .grad by flush_grads().  Maps below 8x8 (inputs smaller than the 256x256 the
                     # networks are built for) have no tensor-core weight-gradient kernel: SIMT kernel, on request
-                    ops.conv_wgrad(spec, xp, dy, dw, allow_simt=a0.h * a0.w < 64)
+                    if _STATE["wgrad_side"]:
+                        from . import lanes
+                        if wside is None:
+                            cur_stream = torch.cuda.current_stream(dev)
+                            wside = lanes.wgrad_stream(cur_stream)
+                        ready = torch.cuda.Event()
+                        ready.record(cur_stream)                  # dY is complete here
+                        wside.wait_event(ready)
+                        with torch.cuda.stream(wside):
+                            ops.conv_wgrad(spec, xp, dy, dw, allow_simt=a0.h * a0.w < 64)
+                        wkeep.append(dy)                          # alive until the side stream is joined below
+                    else:
+                        ops.conv_wgrad(spec, xp, dy, dw, allow_simt=a0.h * a0.w < 64)
                     pc.mark_pending(want_b)
                 if needs_dx(node.inp):
                     pc.refresh(dtype)
@@ -598,7 +618,10 @@ class Plan:
                     # RE-PACK of the filters) starts on the side stream behind the event recorded here -- i.e. behind
                     # this layer's weight-gradient AND data-gradient GEMM, the last readers of the packed filter
                     for t in _TRACKERS:
-                        t.contributed(holder)
+                        t.contributed(holder, wside)
+        if wside is not None:
+            cur_stream.wait_stream(wside)       # the pass's activations and dY buffers are released after this point
+            wkeep.clear()
         if not defer_flush:
             flush_grads()
         res = []
