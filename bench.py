@@ -331,6 +331,11 @@ def run_ours(args):
         # duration is its time on half of the SMs next to whatever the other lane runs, which says nothing about the
         # kernel; at this batch size the two schedules differ by < 1 % in step time.
         lanes.set_enabled(False)
+        wside_prev = plan._STATE["wgrad_side"]
+        plan.set_wgrad_side(False)
+        ov_prev = [(o, o.overlap) for o in (model.optimizer_G, model.optimizer_D)]
+        for o, _ in ov_prev:
+            o.overlap = False
         try:
             prof_runner = GraphedStep(model, {"x": x_dev, "y": y_dev}, warmup=2, profile=True)
             for _ in range(3):
@@ -339,6 +344,9 @@ def run_ours(args):
             del prof_runner
         finally:
             lanes.set_enabled(use_lanes)
+            plan.set_wgrad_side(wside_prev)
+            for o, v in ov_prev:
+                o.overlap = v
     clocks = sampler.stop() if rank == 0 else None
     value = args.global_batch * args.steps / (ms / 1e3)
     e2e_value = args.global_batch * args.steps / (ms_e2e / 1e3)
@@ -383,9 +391,9 @@ def run_ours(args):
                 "traffic_source": "static: ncu --set full capture committed under profiles/ (not measured in this run)",
                 "peak_source": pk["source"],
                 "timing": ("external CUDA events around every launch inside a second, instrumented capture of the same step in "
-                           "the serial schedule (lanes off; bucket tails still on their side streams, so the memory-bound "
-                           "families include some overlap), replayed right after the timed region; the timed graph itself "
-                           "carries no events" if args.graph else
+                           "the fully serial schedule (one stream: lanes, weight-gradient side streams and bucket overlap "
+                           "off, so that a launch's bracketed duration is the kernel's own), replayed right after the timed "
+                           "region; the timed graph itself carries no events" if args.graph else
                            "CUDA events around every launch of the timed steps" +
                            ("; the two lanes run concurrently on half of the SMs each, so a launch's duration is its time on "
                             "its half of the machine" if use_lanes else "")),

@@ -16,6 +16,13 @@
 // the MMAs of the following rows continue.  The filter ((kh*cchunks) x N x 64 bf16) stays resident in shared
 // memory.  A tile of 128 input columns yields 128-kw+1 output columns.
 //
+// Several output rows per MMA: input row rho feeds output row r with tap kh = rho - r, i.e. CONSECUTIVE ring slots take
+// consecutive taps in descending order.  The resident filter is therefore stored tap-descending (block kh-1-khi), so
+// the filter blocks of a run of g consecutive slots are contiguous in shared memory and one MMA with N = g * bn
+// (<= 256) feeds all g accumulators: the 128 x 64 A tile is read once per run instead of once per slot (an MMA with
+// both operands in shared memory costs max(N/2, (4096 + 32 N) / 70) cycles: 88 at N = 64, 175 at N = 256).  Only the
+// first touch of a row (tap 0, first channel chunk: accumulate = 0) and the ring wrap need their own MMA.
+//
 // warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (TMEM lane quadrant = warp & 3).
 #include <stdlib.h>
 
@@ -107,7 +114,7 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int khi = 0; khi < p.kh; ++khi)
         for (int q = 0; q < p.cchunks; ++q)
           for (int kwi = 0; kwi < p.kw; ++kwi)
-            tma_load_2d(bres + static_cast<uint32_t>(khi * p.cchunks + q) * b_chunk + static_cast<uint32_t>(kwi * p.co8) * 128u,
+            tma_load_2d(bres + static_cast<uint32_t>(q * p.kh + (p.kh - 1 - khi)) * b_chunk + static_cast<uint32_t>(kwi * p.co8) * 128u,
                         &tmB, bready_bar, khi * p.kwc_pad + kwi * p.c + q * 64, 0);
       int stage = 0; uint32_t phase = 0;
       for (int item = item_begin; item < item_end; ++item) {
@@ -128,6 +135,7 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(bready_bar, 0);
       int stage = 0; uint32_t phase = 0;
       int slot0 = 0; uint32_t sphase0 = 0;      // ring slot / phase of the current item's output row 0
+      const int maxg = 256 / p.bn;              // ring slots one MMA may span
       for (int item = item_begin; item < item_end; ++item) {
         int img, h0, rows, w0;
         decode(item, img, h0, rows, w0);
@@ -141,22 +149,31 @@ conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint64_t adesc = umma_desc_sw128(base + stage * kAStage, 16, 1024);
             int slot = slot_lo; uint32_t sphase = sphase_lo;
             int khi = rho - r_lo;
-            for (int r = r_lo; r <= r_hi; ++r, --khi) {
+            int r = r_lo;
+            while (r <= r_hi) {
+              // first touch of the newest output row (tap 0, first chunk): its accumulator must have been drained, and
+              // the MMA overwrites instead of accumulating -> always a run of its own
               const bool first = (khi == 0) && (q == 0);
-              if (first) {                 // first touch of this output row: its accumulator must have been drained
+              int g = 1;
+              if (first) {
                 mbar_wait(tempty_bar(slot), sphase ^ 1u);
                 tc_fence_after();
+              } else {
+                while (g < maxg && r + g <= r_hi && slot + g < NS && !((khi - g == 0) && (q == 0))) ++g;
               }
-              const uint64_t bdesc = umma_desc_sw128(bres + static_cast<uint32_t>(khi * p.cchunks + q) * b_chunk, 16, 1024);
+              const uint64_t bdesc = umma_desc_sw128(bres + static_cast<uint32_t>(q * p.kh + (p.kh - 1 - khi)) * b_chunk, 16, 1024);
               const uint32_t d = tmem_base + static_cast<uint32_t>(slot * p.bn);
+              const uint32_t idesc = umma_idesc_bf16(128, g * p.bn, 0, 0);
               if (elect_one_sync()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, p.idesc, (first && k == 0) ? 0u : 1u);
-                if (khi == p.kh - 1 && q == p.cchunks - 1) umma_commit(tfull_bar(slot));   // last tap row: row complete
+                  umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+                // the oldest row of the run (largest tap) completes with its last tap row and chunk
+                if (khi == p.kh - 1 && q == p.cchunks - 1) umma_commit(tfull_bar(slot));
               }
               __syncwarp();
-              if (++slot == NS) { slot = 0; sphase ^= 1u; }
+              r += g; khi -= g; slot += g;
+              if (slot >= NS) { slot -= NS; sphase ^= 1u; }
             }
             if (elect_one_sync()) umma_commit(empty_bar(stage));
             __syncwarp();
