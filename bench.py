@@ -452,7 +452,23 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        try:
+            run_ours(args)
+        finally:
+            _teardown()
+
+
+def _teardown():
+    """Leave NCCL cleanly: every rank drains its device and the group is destroyed before the interpreter exits (rank 0
+    builds the JSON line after the other ranks have returned, so the barrier is what keeps them alive until then)."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        import gc
+        gc.collect()                      # captured graphs that hold NCCL kernels go before the communicator does
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

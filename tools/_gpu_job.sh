@@ -1,8 +1,7 @@
-# round-2 GPU job 14: several output rows per MMA in the 7x7 fold kernel
-timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "conv_layer" > gpurun_out/r2_t14.log 2>&1; echo "conv kernel tests rc=$?"
-grep -E "^FAILED|^ERROR|passed|failed" gpurun_out/r2_t14.log | cut -c1-200 | tail -6
-grep -E "^E  " gpurun_out/r2_t14.log | cut -c1-250 | head -8
-B="--steps 10 --warmup 3 --no-cpu-baseline --gpu-reference 0 --profile 0"
-timeout 300 python bench.py --global-batch 64 $B > gpurun_out/r2_b14_gb64.log 2>&1; echo "gb64 $(tail -1 gpurun_out/r2_b14_gb64.log | cut -c90-200)"
-timeout 300 python bench.py --global-batch 8 $B > gpurun_out/r2_b14_gb8.log 2>&1; echo "gb8 $(tail -1 gpurun_out/r2_b14_gb8.log | cut -c90-200)"
-VCG_BENCH_LAYERS=gpurun_out/r2_layers_b64_v2.txt timeout 300 python bench.py --global-batch 64 --steps 5 --warmup 3 --no-cpu-baseline --gpu-reference 0 > gpurun_out/r2_b14_prof.log 2>&1; grep -E "fold|k7" gpurun_out/r2_layers_b64_v2.txt | cut -c1-150
+# round-2 GPU job 16 (1 GPU): full GPU suite, smoke, default bench line
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/r2_final_pytest.log 2>&1; echo "pytest rc=$? $(tail -1 gpurun_out/r2_final_pytest.log)"
+grep -E "^(FAILED|E  )" gpurun_out/r2_final_pytest.log | head -20
+timeout 300 python __graft_entry__.py smoke > gpurun_out/r2_final_smoke.log 2>&1; echo "smoke rc=$? $(tail -2 gpurun_out/r2_final_smoke.log | cut -c1-200)"
+timeout 600 python bench.py > gpurun_out/r2_final_default.log 2>&1; echo "bench rc=$? $(grep '^{' gpurun_out/r2_final_default.log | cut -c90-220)"
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_final_refarm.log 2>&1; echo "ref arm rc=$? $(grep '^{' gpurun_out/r2_final_refarm.log | cut -c1-200)"
+nvidia-smi --query-gpu=name,memory.used --format=csv,noheader
