@@ -39,6 +39,32 @@ if ROOT not in sys.path:
 GLOBAL_BATCH = 64
 METRIC = "VAE-CycleGAN 256x256 training images/s (CycleVAEGAN, global batch 64)"
 UNIT = "img/s"
+WORKLOAD = ("full VAE-CycleGAN (CycleVAEGAN unpaired: 2 VAE generators + 2 discriminators, cycle+KL+LSGAN) "
+            "256x256 training step")
+# BASELINE.json configs[] (1-based here as in DESIGN.md).  5 is the configuration the metric is quoted on and the default;
+# the others run through the same code with --config N (parity-test configurations; informational bench lines).
+CONFIGS = {
+    5: {"cls": "CycleVAEGAN", "kwargs": {"paired": False}, "batch": GLOBAL_BATCH, "same_xy": False, "metric": METRIC,
+        "workload": WORKLOAD, "latent_dim": 64, "step_flops_b64": 57.8e12},
+    4: {"cls": "CycleVAE", "kwargs": {"paired": False}, "batch": 32, "same_xy": False, "latent_dim": 64,
+        "metric": "Cycle-VAE 256x256 training images/s (CycleVAE unpaired, global batch 32)",
+        "workload": "Cycle-VAE (CycleVAE unpaired: 2 VAE generators, cycle+KL) 256x256 training step"},
+    3: {"cls": "VAEGAN", "kwargs": {}, "batch": 16, "same_xy": False, "latent_dim": 64,
+        "metric": "VAE-GAN 256x256 training images/s (VAEGAN, batch 16)",
+        "workload": "VAE-GAN (VAE generator + discriminator, translation-L1 + KL + LSGAN) 256x256 training step"},
+    2: {"cls": "VariationalAutoencoder", "kwargs": {"latent_dim": 1024}, "batch": 8, "same_xy": True, "latent_dim": 1024,
+        "metric": "VAE 256x256 training images/s (VariationalAutoencoder latent_dim 1024, batch 8)",
+        "workload": "VAE (latent_dim 1024, lambda_kl 1e-5, reconstruction-L1 + KL) 256x256 training step"},
+    1: {"cls": "Autoencoder", "kwargs": {}, "batch": 4, "same_xy": True, "latent_dim": None,
+        "metric": "AE 256x256 training images/s (Autoencoder, batch 4)",
+        "workload": "Autoencoder (reconstruction-L1) 256x256 training step"},
+}
+LOSS_KW = dict(lambda_kl=1e-5, lambda_gan=1.0, lambda_identity=5.0, lambda_cycle=10.0, lambda_recon=1.0)
+
+
+def optimizers(model):
+    """the FusedAdam objects of a composite: (optimizer_G, optimizer_D) or (optimizer,)"""
+    return [o for o in (getattr(model, n, None) for n in ("optimizer_G", "optimizer_D", "optimizer")) if o is not None]
 
 
 def parse():
@@ -47,7 +73,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
+    ap.add_argument("--config", type=int, default=5, choices=sorted(CONFIGS),
+                    help="BASELINE.json configuration (1-based): 5 = full VAE-CycleGAN, global batch 64 (default, the headline)")
+    ap.add_argument("--global-batch", type=int, default=0, help="0: the configuration's own batch")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=2, help="bounded CPU sample: batch of the reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -64,7 +92,11 @@ def parse():
     ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32"], help="gradient all-reduce element type")
     ap.add_argument("--profile", type=int, default=1, help="1: external CUDA events around every launch inside the captured graph")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (vcg_b200.graph.GraphedStep)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.cfg = CONFIGS[args.config]
+    if args.global_batch <= 0:
+        args.global_batch = args.cfg["batch"]
+    return args
 
 
 # ------------------------------------------------------------------------------------ helpers
@@ -113,30 +145,42 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def reference_model(device="cpu"):
+def reference_model(device="cpu", cfg=None):
     """-> (model with training_step, kind, origin).  kind 'reference': the UNMODIFIED reference class
     (Networks.CycleVAEGAN, Networks.py:1872-2150); 'port': the oracle restatement of it (same ATen ops)."""
     import torch
     from oracle import ref_loader
     from oracle import ref_port as rp
+    cfg = cfg or CONFIGS[5]
     net, origin = ref_loader.load()
     torch.manual_seed(1234)
     if net is not None:
-        m = net.CycleVAEGAN(paired=False).to(device)
+        m = getattr(net, cfg["cls"])(**cfg["kwargs"]).to(device)
         m.configure_optimizers(lr=2e-4)
-        m.configure_loss(lambda_kl=1e-5, lambda_gan=1.0, lambda_identity=5.0, lambda_cycle=10.0, lambda_recon=1.0)
+        m.configure_loss(**LOSS_KW)
         m.train()
         return m, "reference", origin
+    if cfg["cls"] != "CycleVAEGAN":
+        raise RuntimeError("the reference modules are not available (oracle/_ref archive missing): only the headline "
+                           "configuration has an oracle-port fallback")
     return rp.RefModel("cyclevaegan", paired=False, lr=2e-4, device=None if device == "cpu" else device), "port", origin
 
 
-def cpu_step_time(batch, steps, warmup):
+def synthetic_batch(rp, cfg, b):
+    batch = rp.synthetic_batch(b)
+    if cfg["same_xy"]:
+        batch["y"] = batch["x"]
+    return batch
+
+
+def cpu_step_time(batch, steps, warmup, cfg=None):
     """The reference's own training_step on the host cores (all of them)."""
     import torch
     from oracle import ref_port as rp
     torch.set_num_threads(os.cpu_count())
-    model, kind, origin = reference_model("cpu")
-    b = rp.synthetic_batch(batch)
+    cfg = cfg or CONFIGS[5]
+    model, kind, origin = reference_model("cpu", cfg)
+    b = synthetic_batch(rp, cfg, batch)
     for _ in range(warmup):
         model.training_step(b)
     ts = []
@@ -147,23 +191,24 @@ def cpu_step_time(batch, steps, warmup):
     return ts, torch.get_num_threads(), kind, origin
 
 
-def gpu_reference(dev, global_batch):
+def gpu_reference(dev, global_batch, cfg=None):
     """Stock PyTorch on the same GPU: the unmodified reference modules, .to(cuda), training_step (train.py:385, 91-97).
     Two modes: as shipped (fp32 tensors, cuDNN TF32 allowed by default) and bf16 autocast + channels_last.
     Largest batch <= global_batch that fits; informational (the reference publishes no GPU number)."""
     import torch
     from oracle import ref_port as rp
     out = {}
+    cfg = cfg or CONFIGS[5]
     for mode in ("fp32_tf32_default", "bf16_autocast_channels_last"):
         b = global_batch
         while b >= 1:
             model = None
             try:
                 torch.cuda.empty_cache()
-                model, kind, origin = reference_model(dev)
+                model, kind, origin = reference_model(dev, cfg)
                 if mode.startswith("bf16") and kind == "reference":
                     model = model.to(memory_format=torch.channels_last)
-                batch = {k: v.to(dev) for k, v in rp.synthetic_batch(b).items()}
+                batch = {k: v.to(dev) for k, v in synthetic_batch(rp, cfg, b).items()}
 
                 def step():
                     if mode.startswith("bf16"):
@@ -193,24 +238,28 @@ def gpu_reference(dev, global_batch):
     return out
 
 
+def _kw(cfg):
+    return ", ".join(f"{k}={v}" for k, v in cfg["kwargs"].items())
+
+
 # ------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ts, threads, kind, origin = cpu_step_time(args.cpu_batch, args.steps, args.warmup)
+    cfg = args.cfg
+    ts, threads, kind, origin = cpu_step_time(args.cpu_batch, args.steps, args.warmup, cfg)
     total = sum(ts)
     value = args.cpu_batch * len(ts) / total
-    sample = (f"CycleVAEGAN(paired=False) training_step, batch {args.cpu_batch} (bounded sample of the global-batch-"
+    sample = (f"{cfg['cls']}({_kw(cfg)}) training_step, batch {args.cpu_batch} (bounded sample of the global-batch-"
               f"{args.global_batch} workload), fp32, {threads} host threads, "
               + (f"the unmodified reference modules ({origin})" if kind == "reference" else "oracle port of the reference"))
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "full VAE-CycleGAN (CycleVAEGAN unpaired: 2 VAE generators + 2 discriminators, cycle+KL+LSGAN) "
-                               "256x256 training step, global batch %d, per-GPU batch %d" % (args.global_batch, args.global_batch // max(1, args.gpus)),
-                   "global_batch": args.global_batch, "parallelism": f"dp{args.gpus}", "latent_dim": 64,
+        "config": {"workload": "%s, global batch %d, per-GPU batch %d" % (cfg["workload"], args.global_batch, args.global_batch // max(1, args.gpus)),
+                   "global_batch": args.global_batch, "parallelism": f"dp{args.gpus}", "latent_dim": cfg["latent_dim"],
                    "cpu_sample_batch": args.cpu_batch,
                    "note": "reference arm: the reference's own CPU path on a bounded batch of the same workload"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
@@ -246,11 +295,13 @@ def run_ours(args):
     lanes.set_enabled(use_lanes)
 
     torch.manual_seed(1234)
-    model = N.CycleVAEGAN(paired=False).to(dev)
+    cfg = args.cfg
+    model = getattr(N, cfg["cls"])(**cfg["kwargs"]).to(dev)
     model.configure_optimizers(lr=2e-4)
-    model.configure_loss(lambda_kl=1e-5, lambda_gan=1.0, lambda_identity=5.0, lambda_cycle=10.0, lambda_recon=1.0)
+    model.configure_loss(**LOSS_KW)
     model.train()
-    for o in (model.optimizer_G, model.optimizer_D):
+    opts = optimizers(model)
+    for o in opts:
         if args.overlap >= 0:
             o.overlap = bool(args.overlap)
         if args.side_streams > 0:
@@ -261,7 +312,7 @@ def run_ours(args):
         sync = vdist.attach(model, vdist.GradSync(wire=args.wire))
     g = torch.Generator().manual_seed(7)
     x_all = torch.rand(args.global_batch, 3, 256, 256, generator=g)
-    y_all = torch.rand(args.global_batch, 3, 256, 256, generator=g)
+    y_all = x_all if cfg["same_xy"] else torch.rand(args.global_batch, 3, 256, 256, generator=g)
     x_host = vdist.shard(x_all, rank, world).contiguous().pin_memory()
     y_host = vdist.shard(y_all, rank, world).contiguous().pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
@@ -333,7 +384,7 @@ def run_ours(args):
         lanes.set_enabled(False)
         wside_prev = plan._STATE["wgrad_side"]
         plan.set_wgrad_side(False)
-        ov_prev = [(o, o.overlap) for o in (model.optimizer_G, model.optimizer_D)]
+        ov_prev = [(o, o.overlap) for o in opts]
         for o, _ in ov_prev:
             o.overlap = False
         try:
@@ -399,30 +450,32 @@ def run_ours(args):
                             "its half of the machine" if use_lanes else "")),
                 "launches_per_step": tc_n / max(1, rec_steps), "share_of_step": tc_ms / max(1, rec_steps) / step_ms,
                 "flops_per_launch": tc_flops / max(1, tc_n), "ms_per_launch": tc_ms / max(1, tc_n),
-                "whole_step_tflops": 57.8e12 * (args.global_batch / 64.0) / world / (step_ms / 1e3) / 1e12,
+                "whole_step_tflops": (cfg["step_flops_b64"] * (args.global_batch / 64.0) / world / (step_ms / 1e3) / 1e12
+                                      if cfg.get("step_flops_b64") else None),
                 "families": {k: {"tflops" if k.startswith("conv_") else "tbytes_per_s":
                                  v[0] / (v[1] / 1e3) / 1e12 if v[1] else 0.0, "ms_per_step": v[1] / rec_steps,
                                  "launches_per_step": v[2] / rec_steps} for k, v in fam.items()}}
     if rank != 0:
         return
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": "full VAE-CycleGAN (CycleVAEGAN unpaired: 2 VAE generators + 2 discriminators, cycle+KL+LSGAN) "
-                               "256x256 training step, global batch %d, per-GPU batch %d" % (args.global_batch, per),
-                   "global_batch": args.global_batch, "parallelism": f"dp{world}", "latent_dim": 64,
-                   "l2": "working set (weights 276 MB bf16 + >10 GB activations per step) exceeds the 126 MB L2; no flush needed",
-                   "dead_passes_skipped": True, "cuda_graph": bool(args.graph), "lanes": use_lanes, "bucket_overlap": bool(model.optimizer_G.overlap),
+        "config": {"workload": "%s, global batch %d, per-GPU batch %d" % (cfg["workload"], args.global_batch, per),
+                   "baseline_config": args.config,
+                   "global_batch": args.global_batch, "parallelism": f"dp{world}", "latent_dim": cfg["latent_dim"],
+                   "l2": ("working set (weights 276 MB bf16 + >10 GB activations per step) exceeds the 126 MB L2; no flush needed"
+                          if args.config == 5 else "weights + saved activations of a step exceed the 126 MB L2; no flush"),
+                   "dead_passes_skipped": True, "cuda_graph": bool(args.graph), "lanes": use_lanes, "bucket_overlap": bool(opts[0].overlap),
                    "gradient_wire": (args.wire if world > 1 else None),
-                   "wire_bytes_per_step_per_rank": (sum(o.flat_grad().numel() for o in (model.optimizer_G, model.optimizer_D)) *
+                   "wire_bytes_per_step_per_rank": (sum(o.flat_grad().numel() for o in opts) *
                                                     (2 if args.wire == "bf16" else 4) if world > 1 else 0)},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "h2d_overlapped_with_previous_step": bool(args.graph)},
         "gpu_launches": launches,
         "clocks": clocks,
-        "final_metrics": {k: last[k] for k in ("G_loss", "D_loss", "loss_cycle", "loss_kl")},
+        "final_metrics": {k: last[k] for k in ("total_loss", "G_loss", "D_loss", "loss_cycle", "loss_kl", "loss_recon") if k in last},
     }
     want_gpu_ref = args.gpu_reference == 1 or (args.gpu_reference < 0 and world == 1)
     if want_gpu_ref:
@@ -432,15 +485,15 @@ def run_ours(args):
         import gc
         gc.collect()
         torch.cuda.empty_cache()
-        line["gpu_reference"] = gpu_reference(dev, args.global_batch)
+        line["gpu_reference"] = gpu_reference(dev, args.global_batch, cfg)
         best = max((v.get("value", 0.0) for v in line["gpu_reference"].values()), default=0.0)
         if best:
             line["gpu_reference"]["ours_over_best_stock_pytorch"] = value / best
     if world == 1 and not args.no_cpu_baseline:
-        ts, threads, kind, origin = cpu_step_time(args.cpu_batch, 6, 1)      # ~11 s of CPU work on the box's host threads
+        ts, threads, kind, origin = cpu_step_time(args.cpu_batch, 6, 1, cfg)      # ~11 s of CPU work on the box's host threads
         v = args.cpu_batch * len(ts) / sum(ts)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
-                                "sample": f"CycleVAEGAN(paired=False) training_step, batch {args.cpu_batch}, fp32, 1 warm-up + "
+                                "sample": f"{cfg['cls']}({_kw(cfg)}) training_step, batch {args.cpu_batch}, fp32, 1 warm-up + "
                                           f"{len(ts)} timed steps ({sum(ts):.1f} s) of " +
                                           (f"the unmodified reference modules ({origin})" if kind == "reference"
                                            else "the oracle port") + " on the host cores"}
