@@ -1,9 +1,6 @@
-# round-2 GPU job 17 (1 GPU): the other BASELINE configurations through bench.py (ours, stock PyTorch on the GPU, CPU reference)
-for c in 2 3 4 1; do
-  timeout 400 python bench.py --config $c --steps 10 --warmup 3 > gpurun_out/r2_cfg${c}_n1.log 2>&1; echo "cfg $c rc=$? $(grep '^{' gpurun_out/r2_cfg${c}_n1.log | python -c "
-import json,sys
-for l in sys.stdin:
-    d=json.loads(l); g=d.get('gpu_reference',{}); print(round(d['value'],1), round(d['ms_per_step'],3), {k:(round(v['value'],1) if isinstance(v,dict) and 'value' in v else v) for k,v in g.items()}, round(d['roofline']['frac'],3), d['cpu_baseline']['value'])
-")"
-  grep -E "Error|error" gpurun_out/r2_cfg${c}_n1.log | head -3
-done
+# round-2 GPU job 18 (4 GPUs): BASELINE configuration 4 (Cycle-VAE unpaired, global batch 32) data-parallel on 2 and 4 GPUs
+T="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+timeout 300 $T --nproc-per-node 2 --master-port 29551 bench.py --config 4 --gpus 2 --steps 10 --warmup 3 --profile 0 > gpurun_out/r2_cfg4_n2.log 2>&1; echo "cfg4 n2 rc=$? $(grep '^{' gpurun_out/r2_cfg4_n2.log | cut -c80-230)"
+timeout 300 $T --nproc-per-node 4 --master-port 29552 bench.py --config 4 --gpus 4 --steps 10 --warmup 3 --profile 0 > gpurun_out/r2_cfg4_n4.log 2>&1; echo "cfg4 n4 rc=$? $(grep '^{' gpurun_out/r2_cfg4_n4.log | cut -c80-230)"
+grep -E "Error|error" gpurun_out/r2_cfg4_n2.log gpurun_out/r2_cfg4_n4.log | head -5
+nvidia-smi --query-gpu=index,memory.used --format=csv,noheader
