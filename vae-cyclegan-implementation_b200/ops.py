@@ -39,6 +39,7 @@ def _rec(kind, flops, tag=""):
         return None
     s = torch.cuda.Event(enable_timing=True, external=_Prof.external)
     s.record()
+    s.vcg_stream = torch.cuda.current_stream().cuda_stream      # which stream the launch went to (tools/step_timeline.py)
     return (kind, flops, tag, s)
 
 
