@@ -185,3 +185,25 @@ def test_data_parallel_sharding_and_loader(vcg, tmp_path):
     batches = list(loader)
     assert len(loader) == 2 and batches[0]["x"].shape == (2, 3, 16, 16) and batches[1]["x"].shape == (1, 3, 16, 16)
     assert torch.equal(batches[0]["x"][0], ds[2]["x"])
+
+
+def test_bench_configurations_cover_baseline_json(N):
+    """bench.py --config N: one entry per BASELINE.json configuration, each naming a constructible composite with the
+    two-method training contract and the batch BASELINE.json quotes."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("vcg_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    base = json.load(open(os.path.join(root, "BASELINE.json")))
+    assert sorted(bench.CONFIGS) == list(range(1, len(base["configs"]) + 1))
+    for i, text in enumerate(base["configs"], start=1):
+        cfg = bench.CONFIGS[i]
+        assert f"batch {cfg['batch']}" in text, (i, text)
+        model = getattr(N, cfg["cls"])(**cfg["kwargs"])
+        model.configure_optimizers(lr=2e-4)
+        model.configure_loss(**bench.LOSS_KW)
+        assert callable(model.training_step) and callable(model.validation_step)
+        assert len(bench.optimizers(model)) == (2 if hasattr(model, "optimizer_D") and model.optimizer_D is not None else 1)
+    assert bench.CONFIGS[5]["metric"] == bench.METRIC and bench.CONFIGS[2]["kwargs"]["latent_dim"] == 1024

@@ -362,6 +362,7 @@ class _Composite(_PlanModule):
 
     def _finish_steps(self):
         """complete optimiser steps whose gradient exchange was left running (data-parallel overlap, dist.py)"""
+        _lanes.join_wgrad()
         for n in ("optimizer", "optimizer_G", "optimizer_D"):
             o = getattr(self, n, None)
             if o is not None and hasattr(o, "finish"):
