@@ -25,6 +25,7 @@ from . import lib as _L
 from .Losses import (CycleConsistencyLoss, GANLossDiscriminator, GANLossGenerator, IdentityLoss,
                      KLDivergenceLoss, TranslationLoss)
 from .functions import require_cuda, run_plan
+from . import functions as _fn
 from .optim import FusedAdam
 from .plan import Plan, PlanBuilder, no_wgrad, _STATE
 from . import plan as _plan
@@ -362,7 +363,6 @@ class _Composite(_PlanModule):
 
     def _finish_steps(self):
         """complete optimiser steps whose gradient exchange was left running (data-parallel overlap, dist.py)"""
-        _lanes.join_wgrad()
         for n in ("optimizer", "optimizer_G", "optimizer_D"):
             o = getattr(self, n, None)
             if o is not None and hasattr(o, "finish"):
@@ -372,6 +372,7 @@ class _Composite(_PlanModule):
         """dict of 0-d tensors -> dict of python floats with ONE device synchronisation (the reference
         pays one .item() sync per metric, Networks.py:2054-2076); averaged over ranks when data-parallel."""
         self._finish_steps()
+        _fn.end_step()
         keys = list(named)
         vals = torch.stack([named[k].detach().float().reshape(()) for k in keys])
         sync = getattr(self, "_vcg_sync", None)
@@ -389,6 +390,7 @@ class _Composite(_PlanModule):
     def _xy(batch):
         x, y = batch["x"], batch["y"]
         require_cuda(x, "batch['x']")
+        _fn.begin_step(x.device)          # one zero-fill for all loss accumulators of the step (functions.py)
         return x, y
 
 

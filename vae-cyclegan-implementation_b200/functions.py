@@ -70,6 +70,31 @@ def _f32c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+# Accumulators of the fused loss kernels (they add block partial sums into a zeroed scalar).  Inside a composite's
+# step (Networks._Composite._xy ... _items) all of them come from ONE arena zeroed by one launch at the start of the
+# step -- a zero-fill launch per loss call sat on the serial section between the forward and the backward pass (12
+# launches of a VAE-CycleGAN step).  Outside a step every call zeroes its own.
+_ARENA = {"buf": None, "pos": 0}
+_ARENA_FLOATS = 512
+
+
+def begin_step(device):
+    _ARENA["buf"] = ops.zero_(torch.empty(_ARENA_FLOATS, dtype=torch.float32, device=device))
+    _ARENA["pos"] = 0
+
+
+def end_step():
+    _ARENA["buf"] = None
+
+
+def _accumulator(device):
+    buf, i = _ARENA["buf"], _ARENA["pos"]
+    if buf is None or buf.device != device or i + 4 > buf.numel():
+        return ops.zero_(torch.empty(4, dtype=torch.float32, device=device))
+    _ARENA["pos"] = i + 4
+    return buf[i:i + 4]
+
+
 class L1MeanFn(torch.autograd.Function):
     """mean |a - b| (nn.L1Loss, Losses.py:21-24): value and sign gradient from one kernel launch."""
 
@@ -77,7 +102,7 @@ class L1MeanFn(torch.autograd.Function):
     def forward(ctx, a, b):
         require_cuda(a, "L1 loss")
         a, b = _f32c(a.detach()), _f32c(b.detach())
-        out = ops.zero_(torch.empty(4, dtype=torch.float32, device=a.device))
+        out = _accumulator(a.device)
         need = any(ctx.needs_input_grad)
         g = torch.empty_like(a) if need else None
         ops.l1_fwd_bwd(a, b, out[0:1], g, 1.0 / a.numel())
@@ -97,7 +122,7 @@ class MseConstFn(torch.autograd.Function):
     def forward(ctx, d, target):
         require_cuda(d, "GAN loss")
         dd = _f32c(d.detach())
-        out = ops.zero_(torch.empty(4, dtype=torch.float32, device=d.device))
+        out = _accumulator(d.device)
         g = torch.empty_like(dd) if ctx.needs_input_grad[0] else None
         ops.mse_const_fwd_bwd(dd, target, out[0:1], g, 1.0 / dd.numel())
         ctx.g = g
@@ -115,7 +140,7 @@ class KlFn(torch.autograd.Function):
     def forward(ctx, mu, lv):
         require_cuda(mu, "KL loss")
         m, l = _f32c(mu.detach()), _f32c(lv.detach())
-        out = ops.zero_(torch.empty(4, dtype=torch.float32, device=m.device))
+        out = _accumulator(m.device)
         need = any(ctx.needs_input_grad)
         gm = torch.empty_like(m) if need else None
         gl = torch.empty_like(l) if need else None

@@ -46,11 +46,8 @@ class GraphedStep:
         if profile:
             ops.prof_begin(external=True)
         n0 = lib.launch_count()
-        # the step is captured on a HIGH-priority stream (kernel nodes inherit it): the short serial sections of the step
-        # (loss kernels between the generator and the discriminator backward) otherwise queue behind the machine-
-        # filling grids of the gradient-bucket tails, which run at default priority on the optimisers' side streams
         try:
-            with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(self.x.device, priority=-1)):
+            with torch.cuda.graph(self.graph):
                 model.training_step(batch)
         finally:
             model._vcg_capture = None

@@ -73,30 +73,6 @@ def wgrad_stream(chain):
     return s
 
 
-_WPENDING = []        # [(side stream, tensors its queued weight-gradient GEMMs read)] not yet joined
-
-
-def defer_wgrad(wside, keep):
-    """plan.run_backward issued weight-gradient GEMMs on `wside` that read the tensors in `keep`.  Their consumers
-    (FusedAdam bucket tails) wait on events of their own, so the pass that issued them does not wait: the tensors stay
-    alive here and the stream is joined by join_wgrad() -- at the end of the training step, or before an untracked
-    gradient flush.  (Joining at the end of every backward pass made the discriminator step of the GAN models wait for
-    the generators' last, low-priority weight gradients: 0.4 ms of a 12.8 ms step at batch 8.)"""
-    _WPENDING.append((wside, list(keep)))
-
-
-def join_wgrad(device=None):
-    """make the current stream wait for every deferred weight-gradient stream, then release the kept tensors"""
-    if _WPENDING:
-        cur = torch.cuda.current_stream(device)
-        seen = set()
-        for s, _ in _WPENDING:
-            if s.device == cur.device and s.cuda_stream not in seen:
-                seen.add(s.cuda_stream)
-                cur.wait_stream(s)
-        _WPENDING[:] = [(s, k) for s, k in _WPENDING if s.device != cur.device]
-
-
 class _Same:
     def __enter__(self):
         return self

@@ -266,9 +266,6 @@ def flush_grads(holders=None):
         pcs = [pc for h in holders for pc in h.__dict__.get("_vcg_packed", {}).values() if pc.pending]
     if not pcs:
         return
-    if holders is None:
-        from . import lanes
-        lanes.join_wgrad()          # weight-gradient GEMMs still running on their side streams (run_backward)
     went, bent = [], []
     for pc in pcs:
         _PENDING.pop(id(pc), None)
@@ -602,7 +599,7 @@ class Plan:
                         wside.wait_event(ready)
                         with torch.cuda.stream(wside):
                             ops.conv_wgrad(spec, xp, dy, dw, allow_simt=a0.h * a0.w < 64)
-                        wkeep += [dy, xp]                         # alive until the side stream is joined (lanes.join_wgrad)
+                        wkeep.append(dy)                          # alive until the side stream is joined below
                     else:
                         ops.conv_wgrad(spec, xp, dy, dw, allow_simt=a0.h * a0.w < 64)
                     pc.mark_pending(want_b)
@@ -623,9 +620,8 @@ class Plan:
                     for t in _TRACKERS:
                         t.contributed(holder, wside)
         if wside is not None:
-            # no join here: the bucket tails wait on the events recorded by contributed(); everything else (an
-            # untracked flush, the end of the training step) joins through lanes.join_wgrad()
-            lanes.defer_wgrad(wside, wkeep)
+            cur_stream.wait_stream(wside)       # the pass's activations and dY buffers are released after this point
+            wkeep.clear()
         if not defer_flush:
             flush_grads()
         res = []
