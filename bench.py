@@ -89,6 +89,7 @@ def parse():
                          "backward pass: 1 on, 0 off (same launches on the calling stream at step()), -1 library default")
     ap.add_argument("--side-streams", type=int, default=0, help="FusedAdam.side_streams (0: library default)")
     ap.add_argument("--wgrad-side", type=int, default=-1, help="plan.set_wgrad_side (-1: library default)")
+    ap.add_argument("--l2-prefetch", type=int, default=-1, help="vcg_set_l2_prefetch (A/B; -1: library default)")
     ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32"], help="gradient all-reduce element type")
     ap.add_argument("--profile", type=int, default=1, help="1: external CUDA events around every launch inside the captured graph")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (vcg_b200.graph.GraphedStep)")
@@ -282,6 +283,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib.load()
+    if args.l2_prefetch >= 0:
+        lib.check(lib.load().vcg_set_l2_prefetch(args.l2_prefetch), "vcg_set_l2_prefetch")
     plan.set_precision(args.precision)
     if args.wgrad_side >= 0:
         plan.set_wgrad_side(bool(args.wgrad_side))

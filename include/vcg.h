@@ -56,6 +56,10 @@ VCG_API long long vcg_launch_count(void);
  * Networks.py:1909-1914) on two streams and gives each half of the machine, so that small-batch layers whose
  * tile count cannot fill 148 SMs run side by side instead of one after the other.                              */
 VCG_API int vcg_set_sm_budget(int32_t sms);
+/* L2 read-ahead of the streaming backward transforms (process-wide, read at launch time): every block issues
+ * cp.async.bulk.prefetch.L2 for the inputs of the pixels it will touch `chunks` iterations ahead (0 = off).  Their
+ * demand loads are register-limited (8 x 16 B in flight per thread); the prefetch keeps HBM -> L2 streaming ahead.  */
+VCG_API int vcg_set_l2_prefetch(int32_t chunks);
 
 /* Multi-tensor variants: ONE launch packs (both layouts) or unpacks every filter of a network.
  * The caller fills d / pointers / accumulate for each job, runs vcg_wjob_plan on the HOST array (it assigns

@@ -111,6 +111,34 @@ def test_xform_fwd_bwd(K, prec, case, folded):
     assert float(dy[:, 0].abs().max()) == 0.0 and float(dy[:, :, -1].abs().max()) == 0.0, "halo must stay zero"
 
 
+def test_l2_read_ahead_changes_no_result(K):
+    """vcg_set_l2_prefetch only moves HBM -> L2 traffic earlier: the backward transforms return the same bits for every
+    read-ahead distance (blocks of several iterations, chunks that wrap image rows, the last partial chunk)."""
+    ops, L = K
+    n, c, h, w, dt = 3, 64, 72, 52, torch.bfloat16
+    y = rnd(n, h, w, c, seed=1).to(dt)
+    dxp = rnd(n, h + 2, w + 2, c, seed=2).to(dt)
+    mr = torch.stack([y.float().sum((1, 2)), (y.float() ** 2).sum((1, 2))], dim=-1).reshape(-1).contiguous()
+    outs = []
+    try:
+        for dist in (0, 1, 4, 16):
+            L.check(L.load().vcg_set_l2_prefetch(dist), "vcg_set_l2_prefetch")
+            dy = torch.full((n, h + 2, w + 2, c), float("nan"), dtype=dt, device="cuda")
+            gs = torch.zeros(n * c * 2, dtype=torch.float32, device="cuda")
+            ops.xform_bwd_gather([(dxp, 0, 1, True)], y, n, h, w, c, dy, 1, mr, 0, 0, gs, None, stats_hw=h * w, clear_halo=True)
+            ops.xform_bwd_norm(y, n, h, w, c, dy, 1, mr, gs, stats_hw=h * w)
+            torch.cuda.synchronize()
+            outs.append(dy.clone())
+        assert L.load().vcg_set_l2_prefetch(17) != 0 and L.load().vcg_set_l2_prefetch(-1) != 0
+    finally:
+        L.check(L.load().vcg_set_l2_prefetch(1), "vcg_set_l2_prefetch")
+    assert torch.isfinite(outs[0].float()).all()
+    for o in outs[1:]:
+        # (the per-channel sums are accumulated with atomics in a launch-dependent order: allow their last bit)
+        assert float((o.float() - outs[0].float()).abs().max()) <= 2e-2 * float(outs[0].float().abs().max())
+        assert (o == outs[0]).float().mean() > 0.99
+
+
 # --------------------------------------------------------------------------------------------
 CONV_CASES = [  # (name, n, H, W, ci_in, co, k, wmap)
     ("p64", 2, 16, 16, 64, 64, 3, 0), ("p128x256", 1, 32, 32, 128, 256, 3, 0), ("p64x128w64", 3, 64, 64, 64, 128, 3, 0),

@@ -1,5 +1,5 @@
 """Micro-benchmark of the memory-bound transform kernels at the shapes of the batch-64 step.
-usage: python tools/bench_xform.py [n]   -> one line per case: us/launch and GB/s (algorithmic bytes)"""
+usage: python tools/bench_xform.py [n] [prefetch distances, e.g. 2,0,4]   -> one line per case: us/launch and GB/s (algorithmic bytes)"""
 import os
 import sys
 
@@ -10,6 +10,7 @@ import vcg_b200  # noqa
 from vcg_b200 import lib as L, ops
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+PF = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1]
 dt = torch.bfloat16
 FWD = [  # mode, pad, c, h, w, norm, act, res
     (2, 1, 64, 256, 256, 1, 0, 0), (0, 3, 64, 256, 256, 1, 0, 0), (1, 1, 128, 128, 128, 1, 0, 0), (2, 1, 128, 128, 128, 1, 0, 0),
@@ -60,13 +61,16 @@ for c, h, w, srcs, norm, act in BWD:
     dy = torch.zeros(n, h + 2, w + 2, c, dtype=dt, device="cuda")
     gs = torch.zeros(n * c * 2, device="cuda") if norm else None
     db = torch.zeros(c, device="cuda")
-    ms = timeit(lambda: ops.xform_bwd_gather(sl, y, n, h, w, c, dy, 1, mr, act, 0, gs, None if norm else db))
-    by = sum(t[0].numel() * 2 for t in sl) + 2 * y.numel() * 2
-    tot += ms
-    print(f"gath modes{[m for m, _ in srcs]} c{c:5d} {h:3d}x{w:3d} norm{norm}: {ms * 1e3:8.1f} us  {by / ms / 1e6:8.0f} GB/s")
-    if norm:
-        ms = timeit(lambda: ops.xform_bwd_norm(y, n, h, w, c, dy, 1, mr, gs, 0, db))
-        by = 3 * y.numel() * 2
-        tot += ms
-        print(f"norm            c{c:5d} {h:3d}x{w:3d}      : {ms * 1e3:8.1f} us  {by / ms / 1e6:8.0f} GB/s")
+    for pf in PF:        # L2 read-ahead distance (vcg_set_l2_prefetch); the first entry is the library default
+        L.check(L.load().vcg_set_l2_prefetch(pf), "vcg_set_l2_prefetch")
+        ms = timeit(lambda: ops.xform_bwd_gather(sl, y, n, h, w, c, dy, 1, mr, act, 0, gs, None if norm else db))
+        by = sum(t[0].numel() * 2 for t in sl) + 2 * y.numel() * 2
+        tot += ms if pf == PF[0] else 0.0
+        print(f"gath modes{[m for m, _ in srcs]} c{c:5d} {h:3d}x{w:3d} norm{norm} pf{pf}: {ms * 1e3:8.1f} us  {by / ms / 1e6:8.0f} GB/s")
+        if norm:
+            ms = timeit(lambda: ops.xform_bwd_norm(y, n, h, w, c, dy, 1, mr, gs, 0, db))
+            by = 3 * y.numel() * 2
+            tot += ms if pf == PF[0] else 0.0
+            print(f"norm            c{c:5d} {h:3d}x{w:3d}       pf{pf}: {ms * 1e3:8.1f} us  {by / ms / 1e6:8.0f} GB/s")
+    L.check(L.load().vcg_set_l2_prefetch(PF[0]), "vcg_set_l2_prefetch")
 print(f"total {tot:.3f} ms")

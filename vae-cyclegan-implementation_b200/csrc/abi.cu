@@ -25,6 +25,14 @@ extern "C" int vcg_set_sm_budget(int32_t sms) {
   g_sm_budget.store(sms);
   return VCG_OK;
 }
+static std::atomic<int> g_l2_prefetch{1};   // measured best on B200 (tools/bench_xform.py: 1 > 2 >> 4, 8)
+extern "C" int vcg_set_l2_prefetch(int32_t chunks) {
+  VCG_REQUIRE(chunks >= 0 && chunks <= 16, VCG_E_INVALID, "set_l2_prefetch: %d chunks (0..16)", chunks);
+  g_l2_prefetch.store(chunks);
+  return VCG_OK;
+}
+int vcg_l2_prefetch() { return g_l2_prefetch.load(std::memory_order_relaxed); }
+
 int vcg_gemm_sms() {
   const int phys = vcg_num_sms(), b = g_sm_budget.load(std::memory_order_relaxed);
   // pairs of CTAs (cta_group::2 kernels) need an even count

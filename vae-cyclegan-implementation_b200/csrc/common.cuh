@@ -46,6 +46,14 @@ static inline int vcg_num_sms() {
 // SMs a persistent tensor-core kernel may occupy: the physical count, or the budget set through vcg_set_sm_budget()
 // (two independent network passes running on two streams each take half of the machine; abi.cu)
 int vcg_gemm_sms();
+// read-ahead distance (loop iterations) of the streaming transform kernels, vcg_set_l2_prefetch() (abi.cu)
+int vcg_l2_prefetch();
+
+// HBM -> L2 read-ahead of a contiguous byte range (16-byte aligned start; the size is rounded down to 16 bytes)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, long long bytes) {
+  const unsigned b = static_cast<unsigned>(bytes) & ~15u;
+  if (b) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(b) : "memory");
+}
 
 // ------------------------------------------------------------------ element traits
 template <typename T> struct Elem;

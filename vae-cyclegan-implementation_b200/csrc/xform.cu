@@ -339,6 +339,7 @@ xform_fwd_shuffle_kernel(const T* __restrict__ src, const float* __restrict__ mr
 struct GSrc { const void* dxp; int mode, pad, c_pitch, folded; };
 struct XbArgs {
   int n, h, w, c, y_c, norm, act, pre_act, dy_halo, dy_c, nsrc, stats_hw, clear_halo;
+  int l2pf;                    // L2 read-ahead distance in loop iterations (xform_bwd_norm_kernel), 0 = off
   GSrc s[3];
 };
 
@@ -564,6 +565,7 @@ struct FSrc {
 };
 struct XgArgs {
   int n, h, w, c, y_c, norm, act, pre_act, dy_halo, dy_c, nsrc, stats_hw, clear_halo;
+  int l2pf;                    // L2 read-ahead distance in loop iterations (vcg_set_l2_prefetch), 0 = off
   FSrc s[3];
 };
 
@@ -738,7 +740,33 @@ xform_bwd_gather_kernel(const __grid_constant__ XgArgs p, const T* __restrict__ 
   if (p.clear_halo && p.dy_halo > 0) clear_halo_share<T>(dy, n, p.h, p.w, p.dy_halo, p.dy_c, ch, blockIdx.x * lanes + pl, gridDim.x * lanes);
   const bool need_y = p.norm || p.act || p.pre_act;
   const float slope_act = act_slope(p.act), slope_pre = act_slope(p.pre_act);
+  // L2 read-ahead.  The demand loads below are register-limited (8 x 16 B in flight per thread, and none while a warp
+  // computes and stores), so HBM -> L2 is kept streaming by bulk prefetches of the contiguous byte ranges the block
+  // touches p.l2pf iterations from now: lane 0 of warp 0 for y, of warps 1.. for the (plain-layout) sources.  Blocks
+  // that cover every channel of their pixels only (c <= 256: the large planes, where the kernel is HBM-bound).
+  const int step = kXbU * lanes;
+  const bool pf_on = p.l2pf > 0 && gridDim.z == 1 && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) <= p.nsrc;
+  auto prefetch = [&](int q0) {
+    if (q0 >= p1) return;
+    const int q1 = min(q0 + step, p1);
+    const int wi = threadIdx.x >> 5;
+    if (wi == 0) {
+      if (need_y) l2_prefetch_bulk(y + (static_cast<size_t>(n) * hw + q0) * p.y_c, static_cast<long long>(q1 - q0) * p.y_c * sizeof(T));
+      return;
+    }
+    const FSrc& fs = p.s[wi - 1];
+    if (fs.shuffle || fs.sh) return;
+    const T* b = static_cast<const T*>(fs.base) + static_cast<size_t>(n) * fs.img_stride;
+    const int h0 = q0 / p.w, w0 = q0 - h0 * p.w, h1 = (q1 - 1) / p.w, w1 = (q1 - 1) - h1 * p.w;
+    const T* a0 = b + ((h0 + fs.hoff) * fs.rs + (w0 + fs.woff) * fs.cs);
+    const T* a1 = b + ((h1 + fs.hoff) * fs.rs + (w1 + fs.woff) * fs.cs) + p.c;
+    l2_prefetch_bulk(a0, (a1 - a0) * static_cast<long long>(sizeof(T)));
+  };
+  int q_ahead = p0;
+  if (pf_on)
+    for (; q_ahead < p0 + p.l2pf * step; q_ahead += step) prefetch(q_ahead);
   for (int pp = p0 + pl; pp < p1; pp += kXbU * lanes) {
+    if (pf_on) { prefetch(q_ahead); q_ahead += step; }
     int hh[kXbU], ww[kXbU];
     float g[kXbU][8];
     Raw8<T> yr[kXbU];
@@ -852,6 +880,24 @@ xform_bwd_norm_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y,
       ldraw(y + (static_cast<size_t>(n) * hw + q) * p.y_c + ch, yr[u]);
     }
   };
+  // L2 read-ahead (see xform_bwd_gather_kernel): lane 0 of warp 0 for y, of warp 1 for the gradient buffer
+  const int step = kXbU * lanes;
+  const bool pf_on = p.l2pf > 0 && gridDim.z == 1 && (threadIdx.x & 31) == 0 && threadIdx.x < 64;
+  auto prefetch = [&](int q0) {
+    if (q0 >= p1) return;
+    const int q1 = min(q0 + step, p1);
+    if (threadIdx.x == 0) {
+      l2_prefetch_bulk(y + (static_cast<size_t>(n) * hw + q0) * p.y_c, static_cast<long long>(q1 - q0) * p.y_c * sizeof(T));
+    } else {
+      const int h0 = q0 / p.w, w0 = q0 - h0 * p.w, h1 = (q1 - 1) / p.w, w1 = (q1 - 1) - h1 * p.w;
+      const T* a0 = dy + ((static_cast<size_t>(n) * hpd + h0 + p.dy_halo) * wpd + w0 + p.dy_halo) * p.dy_c;
+      const T* a1 = dy + ((static_cast<size_t>(n) * hpd + h1 + p.dy_halo) * wpd + w1 + p.dy_halo) * p.dy_c + p.c;
+      l2_prefetch_bulk(a0, (a1 - a0) * static_cast<long long>(sizeof(T)));
+    }
+  };
+  int q_ahead = p0 + step;       // the first chunk's demand loads go out right below
+  if (pf_on)
+    for (; q_ahead < p0 + (1 + p.l2pf) * step; q_ahead += step) prefetch(q_ahead);
   // the first batch of data loads goes out BEFORE the per-channel statistics are fetched: small planes run only a
   // few iterations per block, and the dependent statistics -> data round trips were a quarter of the kernel time
   int pp = p0 + pl;
@@ -884,6 +930,7 @@ xform_bwd_norm_kernel(const __grid_constant__ XbArgs p, const T* __restrict__ y,
       st8<T>(dp[u], g);
     }
     pp += kXbU * lanes;
+    if (pf_on) { prefetch(q_ahead); q_ahead += step; }
     if (pp < p1) issue(pp);
   }
   if (dbias)
@@ -1071,6 +1118,7 @@ static int fill_xb(const vcg_xbwd_desc* d, const vcg_gsrc* srcs, XbArgs& a) {
   a.n = d->n; a.h = d->h; a.w = d->w; a.c = d->c; a.y_c = d->y_c; a.norm = d->norm; a.act = d->act;
   a.pre_act = d->pre_act; a.dy_halo = d->dy_halo; a.dy_c = d->dy_c; a.nsrc = d->nsrc;
   a.stats_hw = d->stats_hw; a.clear_halo = d->clear_halo;
+  a.l2pf = vcg_l2_prefetch();
   for (int k = 0; k < d->nsrc && srcs; ++k) {
     a.s[k].dxp = srcs[k].dxp; a.s[k].mode = srcs[k].mode; a.s[k].pad = srcs[k].pad; a.s[k].c_pitch = srcs[k].c_pitch;
     a.s[k].folded = srcs[k].folded;
@@ -1097,6 +1145,7 @@ extern "C" int vcg_xform_bwd_gather(const vcg_xbwd_desc* d, const vcg_gsrc* srcs
     g.n = d->n; g.h = d->h; g.w = d->w; g.c = d->c; g.y_c = d->y_c; g.norm = d->norm; g.act = d->act;
     g.pre_act = d->pre_act; g.dy_halo = d->dy_halo; g.dy_c = d->dy_c; g.nsrc = d->nsrc;
     g.stats_hw = d->stats_hw; g.clear_halo = d->clear_halo;
+    g.l2pf = vcg_l2_prefetch();
     const size_t es = d->dtype == VCG_F32 ? 4 : 2;
     for (int k = 0; k < d->nsrc; ++k) {
       FSrc& f = g.s[k];

@@ -70,6 +70,7 @@ _SIGS = {
     "vcg_last_error": (C.c_char_p, []),
     "vcg_launch_count": (C.c_longlong, []),
     "vcg_set_sm_budget": (C.c_int, [i32]),
+    "vcg_set_l2_prefetch": (C.c_int, [i32]),
     "vcg_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vcg_conv_wgrad": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, C.c_void_p]),
     "vcg_wpack": (C.c_int, [C.POINTER(WpackDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
