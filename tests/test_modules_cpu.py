@@ -143,3 +143,28 @@ def test_fused_adam_keeps_torch_adam_interface(N):
         p.grad = torch.zeros_like(p)
     with pytest.raises(RuntimeError, match="CUDA"):
         opt.step()
+
+
+def test_gradient_buckets_partition_the_parameters_in_backward_order(N):
+    """FusedAdam.set_owners / _build_buckets: every parameter in exactly one bucket, one owner per bucket, buckets of
+    an owner in backward-completion order (reverse definition order), at most BUCKET_PARAMS parameters unless a single
+    layer is larger, holders listed with every bucket (what plan.run_backward's contributed() calls count down)."""
+    from vcg_b200 import optim
+    m = N.CycleVAEGAN(paired=False)
+    m.configure_optimizers(lr=2e-4)
+    for opt, owners in ((m.optimizer_G, [m.F, m.G]), (m.optimizer_D, [m.DX, m.DY])):
+        opt._build_buckets()
+        seen = []
+        for b in opt._buckets:
+            assert b.owner is not None and b.holders, "every parameter of these models belongs to an announced owner"
+            n = sum(p.numel() for p in b.params)
+            assert n <= optim.BUCKET_PARAMS or len(b.holders) == 1
+            assert {id(p) for h in b.holders for p in h.parameters(recurse=False)} == {id(p) for p in b.params}
+            seen += [id(p) for p in b.params]
+        assert sorted(seen) == sorted(id(p) for g in opt.param_groups for p in g["params"]) and len(seen) == len(set(seen))
+        assert [b.owner for b in opt._buckets] == sorted((b.owner for b in opt._buckets), key=owners.index)
+        for owner in owners:
+            order = [id(h) for b in opt._buckets if b.owner is owner for h in b.holders]
+            defined = [id(h) for h in owner.modules() if getattr(h, "_vcg_holder", False)]
+            assert order == defined[::-1]
+    assert len([b for b in m.optimizer_G._buckets if b.owner is m.G]) == 3 and len(m.optimizer_D._buckets) == 2
