@@ -207,3 +207,37 @@ def test_bench_configurations_cover_baseline_json(N):
         assert callable(model.training_step) and callable(model.validation_step)
         assert len(bench.optimizers(model)) == (2 if hasattr(model, "optimizer_D") and model.optimizer_D is not None else 1)
     assert bench.CONFIGS[5]["metric"] == bench.METRIC and bench.CONFIGS[2]["kwargs"]["latent_dim"] == 1024
+
+
+def test_inference_entry_finds_runs_and_loads_reference_checkpoints(vcg, N, tmp_path):
+    """test.py of the reference (test.py:31-70, 110-142): run discovery by args.json + best_model.pth, model rebuilt from
+    the checkpoint's own args in eval mode, comparison strip written (the forward pass itself needs the GPU)."""
+    from vcg_b200 import test as T
+    from vcg_b200 import utils as U
+    import argparse
+    import json
+    runs = tmp_path / "runs"
+    good, bad = runs / "vae_0101_0000_x_to_y_synthetic", runs / "no_checkpoint_here"
+    good.mkdir(parents=True)
+    bad.mkdir()
+    args = argparse.Namespace(architecture="vae", paired=False, latent_dim=32, dataset="synthetic", image_size=256, lr=2e-4)
+    with open(good / "args.json", "w") as f:
+        json.dump(vars(args), f)
+    with open(bad / "args.json", "w") as f:
+        json.dump(vars(args), f)
+    torch.manual_seed(5)
+    src = N.VariationalAutoencoder(latent_dim=32)
+    src.configure_optimizers(lr=2e-4)
+    U.save_checkpoint(src, 7, 0.5, args, good / "best_model.pth")
+    found = T.discover_runs(runs)
+    assert [r["name"] for r in found] == [good.name] and found[0]["architecture"] == "vae"
+    assert T.discover_runs(tmp_path / "missing") == []
+    m = T.load_model_for_inference("vae", found[0]["checkpoint"], torch.device("cpu"))
+    assert type(m).__name__ == "VariationalAutoencoder" and m.latent_dim == 32 and not m.training
+    for (k, a), (_, b) in zip(sorted(src.state_dict().items()), sorted(m.state_dict().items())):
+        assert torch.equal(a, b), k
+    x = torch.rand(3, 3, 16, 16)
+    T.save_strip(tmp_path / "strip.png", x, x * 0.5, 1.0 - x, max_samples=2)
+    from PIL import Image
+    assert Image.open(tmp_path / "strip.png").size == (48, 32)
+    assert T.build_parser().parse_args([]).num_samples == 8
