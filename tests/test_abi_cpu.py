@@ -21,6 +21,13 @@ def test_header_declares_expected_surface():
     assert len(syms) >= 24
 
 
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md is the maintainer-facing map of the boundary: every declared entry point appears in it"""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [s for s in declared_symbols() if s not in doc]
+    assert not missing, missing
+
+
 def test_library_exports_every_declared_symbol(vcg):
     from vcg_b200 import lib
     out = subprocess.run(["nm", "-D", lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
