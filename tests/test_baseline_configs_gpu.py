@@ -138,7 +138,9 @@ def _check(case, prec, res, mtol, gtol, gcos):
                 # noisy gradient sign) 2e-2
                 bound = (2e-3 if s == 0 else 2e-2) * max(ref, 1e-3) + 1e-6
             elif s == 0:
-                bound = 8e-2 * max(ref, 1e-2) + 2e-3
+                # measured 3.2e-2 .. 7.9e-2 over the three configurations (the run-to-run summation order of the
+                # atomics moves them): 1.5 x the worst observed
+                bound = 1.2e-1 * max(ref, 1e-2) + 2e-3
             else:
                 # discriminator scalars after the update: a 131072-term dot product of normalised features of images
                 # produced by weights that differ by +-lr per element (Adam's first step is sign-like).  Measured against
