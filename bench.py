@@ -508,10 +508,9 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        try:
-            run_ours(args)
-        finally:
-            _teardown()
+        run_ours(args)
+        _teardown()         # success path only: after an exception the other ranks may sit in a collective, and a barrier
+                            # here would hang until the NCCL timeout -- let the launcher tear the group down instead
 
 
 def _teardown():
